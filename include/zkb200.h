@@ -1,0 +1,169 @@
+/*
+ * zkb200 — C ABI of the B200-native STARK proving backend (libzkb200.so).
+ *
+ * This is the drop-in boundary for the Winterfell 0.12 `Prover` plug-in points the reference uses.
+ * The reference is Rust (no cargo/rustc in the build image), so the boundary is this C ABI; the Rust
+ * glue that binds it is shown in INTEGRATION.md and rust/zkb200-winterfell/.  Citations are relative
+ * to /root/reference.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative zkb_status on failure; the message is
+ *     available through zkb_last_error(ctx) (or zkb_last_error(NULL) for context creation);
+ *     nothing panics or throws across the boundary;
+ *   - field elements are 16-byte little-endian canonical values of
+ *     p = 2^128 - 45*2^40 + 1 (winter-math f128::BaseElement, src/training/prover.rs:9);
+ *     digests are 32-byte BLAKE3 outputs (Blake3_256<Felt>, src/training/prover.rs:225);
+ *   - the caller owns every host buffer; the library owns all device memory until zkb_ctx_destroy;
+ *   - a context is bound to one device and one stream and must be used from one thread at a time;
+ *     different contexts may be used concurrently;
+ *   - there is no CPU fallback: without a CUDA device every call fails with ZKB_ERR_CUDA.
+ */
+#ifndef ZKB200_H
+#define ZKB200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zkb_ctx zkb_ctx;
+
+typedef enum {
+    ZKB_OK = 0,
+    ZKB_ERR_INVALID = -1, /* bad argument / unsupported option (the reference panics: src/training/prover.rs:59-61) */
+    ZKB_ERR_CUDA = -2,    /* CUDA runtime failure, including "no device" */
+    ZKB_ERR_STATE = -3,   /* staged call out of order */
+    ZKB_ERR_OOM = -4
+} zkb_status;
+
+/* AIRs on the hot path */
+#define ZKB_AIR_ID_TRAINING 1u    /* src/training/air.rs:105-287   */
+#define ZKB_AIR_ID_AGGREGATION 2u /* src/aggregation/air.rs:93-147 */
+#define ZKB_AIR_ID_MIMC 3u        /* defined by this build from src/helper.rs:213-220,404-406 */
+
+/*
+ * Everything `Prover::prove` derives from (Air, ProofOptions, PublicInputs):
+ *   options       winterfell::ProofOptions::new argument order, src/main.rs:98-107
+ *   pub_elems     PublicInputs::to_elements(): src/training/air.rs:70-94, src/aggregation/air.rs:57-81
+ *   assertions    Air::get_assertions(): src/training/air.rs:130-151, src/aggregation/air.rs:121-147
+ *   params        aggregation: the scaling factor k (src/aggregation/air.rs:108);
+ *                 mimc: the periodic round-constant column (power-of-two length)
+ */
+typedef struct {
+    uint32_t air_id, trace_width;
+    uint64_t trace_len;
+    uint32_t num_queries, blowup, grinding_bits, field_extension, folding, rem_max_degree, batching_constraints,
+        batching_deep;
+    const uint8_t* pub_elems;
+    uint64_t n_pub_elems;
+    const uint32_t* assert_cols;
+    const uint64_t* assert_steps;
+    const uint8_t* assert_values;
+    uint64_t n_assertions;
+    const uint8_t* params;
+    uint64_t n_params;
+} zkb_air_desc;
+
+/* Fiat-Shamir transcript of one proof, exported for stage-by-stage parity checks */
+typedef struct {
+    uint8_t trace_root[32], constraint_root[32], remainder_commitment[32];
+    uint8_t constraint_alpha[16], z[16], deep_alpha[16];
+    uint32_t n_fri_layers, n_positions;
+    uint8_t fri_roots[16][32];
+    uint8_t fri_alphas[16][16];
+    uint64_t pow_nonce;
+    uint32_t positions[256];
+    int32_t comp_degree_ok, _pad;
+} zkb_transcript;
+
+/* per-stage device time of the last proof, milliseconds (CUDA events on the context's stream) */
+typedef struct {
+    float h2d, interpolate, lde, leaf_hash, merkle, constraints, composition, ood, deep, fri, grind, queries, total;
+} zkb_stage_times;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+/* stream: a cudaStream_t (or NULL for the default stream) the caller wants all work issued on */
+int32_t zkb_ctx_create(int32_t device, void* stream, zkb_ctx** out);
+void zkb_ctx_destroy(zkb_ctx* ctx);
+const char* zkb_last_error(const zkb_ctx* ctx);
+/* number of kernels the context has launched so far (evidence for bench.py's gpu_launches) */
+uint64_t zkb_kernel_launches(const zkb_ctx* ctx);
+int32_t zkb_last_stage_times(const zkb_ctx* ctx, zkb_stage_times* out);
+/* pinned host memory for trace columns (fast H2D); plain malloc'ed memory works too, only slower */
+void* zkb_host_alloc(size_t bytes);
+void zkb_host_free(void* p);
+
+/* ---- Prover::prove (src/main.rs:228,424,468; src/training/prover.rs:221-301) ------------------------- */
+/*
+ * cols: trace_width host pointers, column j = trace_len elements (TraceTable columns, column-major).
+ * force_nonce: 0 = grind for the smallest valid nonce (non-`concurrent` Winterfell); otherwise use it.
+ * proof_out: Proof::to_bytes() layout, allocated by the library; release with zkb_free.
+ */
+int32_t zkb_prove(zkb_ctx* ctx, const zkb_air_desc* air, const uint8_t* const* cols, uint64_t force_nonce,
+                  uint8_t** proof_out, uint64_t* proof_len, zkb_transcript* transcript);
+/* same, with the column-major trace [w][n] already resident in device memory */
+int32_t zkb_prove_device(zkb_ctx* ctx, const zkb_air_desc* air, const void* d_trace_colmajor, uint64_t force_nonce,
+                         uint8_t** proof_out, uint64_t* proof_len, zkb_transcript* transcript);
+void zkb_free(void* p);
+
+/* ---- staged surface: the three associated types + the stages inside Prover::prove ------------------------
+ * Order: begin -> trace_commit -> constraints_eval -> constraints_commit -> ood_eval -> deep_compose
+ *        -> { fri_commit_layer, fri_fold }* -> fri_remainder -> grind -> query -> (next begin)
+ */
+int32_t zkb_begin(zkb_ctx* ctx, const zkb_air_desc* air);
+/* Prover::new_trace_lde -> DefaultTraceLde::new (src/training/prover.rs:273-281): K1-K4 */
+int32_t zkb_trace_commit(zkb_ctx* ctx, const uint8_t* const* cols, uint8_t root_out[32]);
+int32_t zkb_trace_commit_device(zkb_ctx* ctx, const void* d_trace_colmajor, uint8_t root_out[32]);
+/* TraceLde::read_main_trace_frame_into: current and next row of LDE step `lde_step` */
+int32_t zkb_trace_read_frame(zkb_ctx* ctx, uint64_t lde_step, uint8_t* current_out, uint8_t* next_out);
+/* TracePolyTable contents, row-major [n][w] coefficients (only needed if the host keeps DEEP) */
+int32_t zkb_trace_polys_read(zkb_ctx* ctx, uint8_t* out);
+/* Prover::new_evaluator + ConstraintEvaluator::evaluate (src/training/prover.rs:283-290): K5.
+ * alpha: the single draw of ConstraintCompositionCoefficients::draw_algebraic.
+ * evals_out (optional): CompositionPolyTrace, ce_blowup*trace_len elements. */
+int32_t zkb_constraints_eval(zkb_ctx* ctx, const uint8_t alpha[16], uint8_t* evals_out);
+/* Prover::build_constraint_commitment -> DefaultConstraintCommitment::new (src/training/prover.rs:292-300): K6 */
+int32_t zkb_constraints_commit(zkb_ctx* ctx, uint8_t root_out[32]);
+/* TracePolyTable::get_ood_frame + CompositionPoly::evaluate_at: K7.  cur/next: w elements, h: c elements */
+int32_t zkb_ood_eval(zkb_ctx* ctx, const uint8_t z[16], uint8_t* cur_out, uint8_t* next_out, uint8_t* h_out);
+/* DeepCompositionPoly::{add_trace_polys, add_composition_poly, evaluate}: K8; alpha = the DEEP draw */
+int32_t zkb_deep_compose(zkb_ctx* ctx, const uint8_t deep_alpha[16]);
+/* FriProver::build_layers, one layer at a time: K9 */
+int32_t zkb_fri_num_layers(zkb_ctx* ctx, uint32_t* out);
+int32_t zkb_fri_commit_layer(zkb_ctx* ctx, uint8_t root_out[32]);
+int32_t zkb_fri_fold(zkb_ctx* ctx, const uint8_t alpha[16]);
+/* remainder coefficients in Winterfell's (reversed) order; n_coeffs_out elements */
+int32_t zkb_fri_remainder(zkb_ctx* ctx, uint8_t* coeffs_out, uint64_t* n_coeffs_out, uint8_t commitment_out[32]);
+/* ProverChannel::grind_query_seed: smallest nonce >= 1 with >= bits trailing zeros: K10 */
+int32_t zkb_grind(zkb_ctx* ctx, const uint8_t seed[32], uint32_t bits, uint64_t* nonce_out);
+/* TraceLde::query / ConstraintCommitment::query / FriProver::build_proof: K11.
+ * which: 0 = trace, 1 = constraint composition, 2+l = FRI layer l (positions already folded by the caller).
+ * rows_out: n_pos rows, row-major; proof_out: BatchMerkleProof::to_bytes(), allocated by the library. */
+int32_t zkb_query(zkb_ctx* ctx, uint32_t which, const uint32_t* positions, uint32_t n_pos, uint8_t* rows_out,
+                  uint8_t** proof_out, uint64_t* proof_len);
+
+/* ---- helpers next to the path ---------------------------------------------------------- */
+/* device-side MiMC chain trace; out_cols_colmajor: w*n elements, host memory */
+int32_t zkb_mimc_trace(zkb_ctx* ctx, const uint8_t* seeds, uint32_t w, uint64_t n, const uint8_t* round_constants,
+                       uint32_t n_rc, uint8_t* out_colmajor);
+/* same, leaving the trace in device memory; returns the device pointer (owned by the context) */
+int32_t zkb_mimc_trace_device(zkb_ctx* ctx, const uint8_t* seeds, uint32_t w, uint64_t n, const uint8_t* round_constants,
+                              uint32_t n_rc, void** d_out);
+/* upload a column-major host trace into a context-owned device buffer (for device-resident timing) */
+int32_t zkb_upload_trace(zkb_ctx* ctx, const uint8_t* const* cols, uint32_t w, uint64_t n, void** d_out);
+
+/* ---- self-test kernels for KATs (field ops and hash_elements on the device) ------------------------------ */
+int32_t zkb_test_field(zkb_ctx* ctx, const uint8_t* a, const uint8_t* b, uint32_t n, uint8_t* mul_out, uint8_t* add_out,
+                       uint8_t* sub_out, uint8_t* inv_out);
+int32_t zkb_test_hash_elements(zkb_ctx* ctx, const uint8_t* rows, uint32_t elems_per_row, uint32_t n_rows,
+                               uint8_t* digests_out);
+int32_t zkb_test_merkle_root(zkb_ctx* ctx, const uint8_t* leaves, uint64_t n_leaves, uint8_t root_out[32]);
+/* LDE of a column-major host matrix: out row-major [n*blowup][w] (for parity tests of K1+K2) */
+int32_t zkb_test_lde(zkb_ctx* ctx, const uint8_t* const* cols, uint32_t w, uint64_t n, uint32_t blowup, uint8_t* polys_out,
+                     uint8_t* lde_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKB200_H */

@@ -1,0 +1,96 @@
+"""Shared seeded inputs for the parity tests (none of the reference's thread_rng sites are used)."""
+import random
+
+import numpy as np
+
+import zk_stark_project_b200 as Z
+from zk_stark_project_b200 import field as F
+from zk_stark_project_b200.training import AC, FE
+
+P = Z.P
+
+
+def splitmix(seed):
+    state = seed & 0xFFFFFFFFFFFFFFFF
+
+    def nxt():
+        nonlocal state
+        state = (state + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        z = state
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        return z ^ (z >> 31)
+    return nxt
+
+
+def random_felts(count, seed):
+    """uniform-ish elements below p as a (count, 2) uint64 array (hi word < 2^64 - 1 keeps them canonical)."""
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 1 << 64, size=(count, 2), dtype=np.uint64)
+    a[:, 1] &= np.uint64(0x7FFFFFFFFFFFFFFF)
+    return a
+
+
+def options(blowup=16, queries=40, grinding=8):
+    return Z.ProofOptions(queries, blowup, grinding, Z.FieldExtension.NONE, 16, 7)
+
+
+def model(rng, sigma):
+    w = [[F.f64_to_signed_felt(rng.gauss(0, sigma), 1e6) for _ in range(FE)] for _ in range(AC)]
+    b = [F.f64_to_signed_felt(rng.gauss(0, sigma), 1e6) for _ in range(AC)]
+    return ([[v for v, _ in r] for r in w], [[s for _, s in r] for r in w], [v for v, _ in b], [s for _, s in b])
+
+
+def training_prover(bs, opts, seed=0x5EED0002):
+    """tests/integration_tests.rs:14-58 shaped inputs, but seeded."""
+    rng = random.Random(seed)
+    w, ws, b, bs_ = model(rng, 1.0)
+    x = [[Z.f64_to_felt((i + j) * 0.1) for j in range(FE)] for i in range(bs)]
+    xs = [[0] * FE for _ in range(bs)]
+    y = [[Z.f64_to_felt(1.0) if a == i % AC else 0 for a in range(AC)] for i in range(bs)]
+    return Z.TrainingUpdateProver(opts, w, b, ws, bs_, x, xs, y, Z.f64_to_felt(0.01), Z.f64_to_felt(1e6), bs, seed=seed)
+
+
+def aggregation_prover(num_updates, opts, seed=0x5EED0003):
+    """src/main.rs:440-459 shaped inputs, but seeded."""
+    rng = random.Random(seed)
+    gw, _, gb, _ = model(rng, 10000.0)
+    reps = [rng.randrange(2**64) for _ in range(num_updates)]
+    lw = [[[Z.f64_to_felt(r / 1e6)] * FE for _ in range(AC)] for r in reps]
+    lb = [[Z.f64_to_felt(r / 1e6)] * AC for r in reps]
+    return Z.GlobalUpdateProver(opts, gw, gb, lw, lb, Z.f64_to_felt(float(num_updates)), seed=seed)
+
+
+def mimc_prover(width, steps, opts):
+    return Z.MimcProver(opts, [j + 1 for j in range(width)], steps)
+
+
+def synthetic_training_air(n, opts, data):
+    """Training-shaped AIR over an arbitrary 240-column trace (the prover is data-oblivious):
+    `data` is the (240, n, 2) uint64 trace; batch_size chosen so the reference would pick this trace length."""
+    w = data.shape[0]
+    half = w // 2
+    get = lambda c, r: int(data[c, r, 0]) | (int(data[c, r, 1]) << 64)
+    bs = max(1, n // (2 * 60)) if n > 16 else 1
+    while max(1 << (2 * 60 * bs - 1).bit_length(), 16) > n and bs > 1:
+        bs -= 1
+    x = [[Z.f64_to_felt((i + j) * 0.1) for j in range(FE)] for i in range(bs)]
+    y = [[Z.f64_to_felt(1.0) if a == i % AC else 0 for a in range(AC)] for i in range(bs)]
+    pub = Z.TrainingUpdateInputs([get(c, 0) for c in range(half)], [get(c, n - 1) for c in range(half)], n - 1, x, y,
+                                 Z.f64_to_felt(0.01), Z.f64_to_felt(1e6), bs)
+    return Z.TrainingUpdateAir(w, n, pub, opts).describe()
+
+
+TS_FIELDS = ["trace_root", "constraint_alpha", "constraint_root", "z", "deep_alpha", "n_fri_layers", "fri_roots", "fri_alphas",
+             "remainder_commitment", "pow_nonce", "n_positions", "positions"]
+
+
+def transcript_diff(a, b):
+    """First field where two transcripts (oracle / product ctypes structs with identical layout) differ."""
+    for f in TS_FIELDS:
+        x, y = getattr(a, f), getattr(b, f)
+        xb = bytes(x) if hasattr(x, "__len__") else x
+        yb = bytes(y) if hasattr(y, "__len__") else y
+        if xb != yb:
+            return f
+    return None

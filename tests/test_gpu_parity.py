@@ -1,0 +1,198 @@
+"""GPU parity tests: every stage of the CUDA path against the CPU oracle, through the C ABI (libzkb200.so)."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+import zk_stark_project_b200 as Z
+from zk_stark_project_b200 import lib as L
+from tests import common as T
+
+pytestmark = pytest.mark.gpu
+P = Z.P
+
+
+def test_field_kat(gpu_ctx, oracle):
+    rng = random.Random(11)
+    edge = [0, 1, 2, P - 1, P - 2, 2**127, 2**64, 2**64 - 1, 45 * 2**40 - 1, 45 * 2**40, 2**96, P >> 1]
+    a = edge * len(edge) + [rng.randrange(P) for _ in range(4000)]
+    b = [y for y in edge for _ in edge] + [rng.randrange(P) for _ in range(4000)]
+    n = len(a)
+    ab = b"".join(L.fe_bytes(x) for x in a)
+    bb = b"".join(L.fe_bytes(x) for x in b)
+    outs = [C.create_string_buffer(16 * n) for _ in range(4)]
+    gpu_ctx.check(gpu_ctx.lib.zkb_test_field(gpu_ctx.handle, ab, bb, C.c_uint32(n), *outs))
+    mul, add, sub, inv = [[L.fe_int(o.raw[16 * i:16 * i + 16]) for i in range(n)] for o in outs]
+    for i in range(n):
+        assert mul[i] == a[i] * b[i] % P, (a[i], b[i])
+        assert add[i] == (a[i] + b[i]) % P
+        assert sub[i] == (a[i] - b[i]) % P
+        assert inv[i] == (pow(a[i], P - 2, P) if a[i] else 0)
+    # and against the oracle's field
+    for i in range(0, n, 97):
+        assert mul[i] == oracle.fe_op("mul", a[i], b[i])
+
+
+@pytest.mark.parametrize("count", [1, 2, 3, 4, 5, 6, 7, 16, 60, 63, 64, 65, 120, 127, 128, 129, 192, 193, 240, 255])
+def test_hash_elements(gpu_ctx, oracle, count):
+    """Blake3_256::hash_elements for every leaf shape on the path and the chunk boundaries around them."""
+    rows = 37
+    data = T.random_felts(rows * count, 1000 + count).tobytes()
+    out = C.create_string_buffer(32 * rows)
+    gpu_ctx.check(gpu_ctx.lib.zkb_test_hash_elements(gpu_ctx.handle, data, C.c_uint32(count), C.c_uint32(rows), out))
+    for r in range(rows):
+        assert out.raw[32 * r:32 * r + 32] == oracle.blake3(data[r * count * 16:(r + 1) * count * 16]), (count, r)
+
+
+@pytest.mark.parametrize("n", [2, 4, 64, 1024, 4096])
+def test_merkle_root(gpu_ctx, oracle, n):
+    leaves = np.random.default_rng(n).integers(0, 256, size=(n, 32), dtype=np.uint8)
+    root = C.create_string_buffer(32)
+    gpu_ctx.check(gpu_ctx.lib.zkb_test_merkle_root(gpu_ctx.handle, leaves.tobytes(), C.c_uint64(n), root))
+    assert root.raw == oracle.merkle_root([leaves[i].tobytes() for i in range(n)])
+
+
+LDE_CASES = [(8, 1, 2), (8, 3, 8), (16, 5, 16), (32, 120, 16), (64, 17, 8), (128, 240, 16), (256, 16, 4), (512, 33, 2),
+             (1024, 64, 8), (4096, 9, 16), (8192, 20, 8), (1 << 14, 2, 16), (1 << 16, 4, 4)]
+
+
+@pytest.mark.parametrize("n,w,blowup", LDE_CASES)
+def test_interpolate_and_lde(gpu_ctx, oracle, n, w, blowup):
+    """K1 + K2 against winter-math's interpolate_poly / evaluate_poly_with_offset (oracle), every pass plan:
+    single pass (n <= 2^8 with 16-column tiles), two passes, narrow-column tiles, ragged column tiles."""
+    data = T.random_felts(w * n, 7 * n + w).reshape(w, n, 2)
+    buf = np.ascontiguousarray(data)
+    cols = (C.c_void_p * w)(*[buf.ctypes.data + j * n * 16 for j in range(w)])
+    polys = C.create_string_buffer(16 * n * w)
+    lde = C.create_string_buffer(16 * n * w * blowup)
+    gpu_ctx.check(gpu_ctx.lib.zkb_test_lde(gpu_ctx.handle, cols, C.c_uint32(w), C.c_uint64(n), C.c_uint32(blowup), polys, lde))
+    root, o_lde, o_polys = oracle.trace_commit(buf.tobytes(), n, w, blowup, want_lde=True, want_polys=True)
+    # oracle polys are column-major [w][n]; the product keeps them row-major [n][w]
+    got = np.frombuffer(polys.raw, dtype=np.uint64).reshape(n, w, 2).transpose(1, 0, 2)
+    exp = np.frombuffer(o_polys, dtype=np.uint64).reshape(w, n, 2)
+    assert np.array_equal(got, exp), "interpolated polynomials differ"
+    assert lde.raw == o_lde, "LDE differs"
+
+
+def _prove_both(gpu_ctx, oracle, air, trace):
+    proof_o, ts_o, _ = oracle.prove(air, trace.to_bytes())
+    data = np.ascontiguousarray(trace.data)
+    proof_g, ts_g = gpu_ctx.prove_host(air, data.ctypes.data)
+    diff = T.transcript_diff(ts_o, ts_g)
+    assert diff is None, f"transcripts diverge at `{diff}`"
+    assert proof_g == proof_o, "proof bytes differ although the transcript matches"
+    oracle.verify(air, proof_g)
+    return proof_g
+
+
+@pytest.mark.parametrize("width,steps,blowup", [(1, 64, 8), (4, 64, 8), (64, 256, 8), (3, 1024, 16), (8, 1 << 14, 8)])
+def test_mimc_proof_parity(gpu_ctx, oracle, width, steps, blowup):
+    p = T.mimc_prover(width, steps, T.options(blowup=blowup))
+    if steps <= 1024:
+        trace = p.build_trace()
+    else:
+        raw = oracle.mimc_trace(p.seeds, steps, p.rc)
+        trace = Z.TraceTable(np.frombuffer(raw, dtype=np.uint64).reshape(width, steps, 2))
+    _prove_both(gpu_ctx, oracle, p.describe(trace), trace)
+
+
+def test_mimc_device_trace(gpu_ctx, oracle):
+    rc = Z.get_round_constants()
+    seeds = [3, 5, 7]
+    assert gpu_ctx.mimc_trace(seeds, 512, rc) == oracle.mimc_trace(seeds, 512, rc)
+
+
+@pytest.mark.parametrize("updates", [1, 6, 16, 30])
+def test_aggregation_proof_parity(gpu_ctx, oracle, updates):
+    p = T.aggregation_prover(updates, T.options())
+    trace = p.build_trace()
+    _prove_both(gpu_ctx, oracle, p.describe(trace), trace)
+
+
+@pytest.mark.parametrize("bs", [1, 2, 5])
+def test_training_proof_parity(gpu_ctx, oracle, bs):
+    p = T.training_prover(bs, T.options())
+    trace = p.build_trace()
+    _prove_both(gpu_ctx, oracle, p.describe(trace), trace)
+
+
+def test_training_reference_options_bs1(gpu_ctx, oracle):
+    """The exact ProofOptions of src/main.rs:98-107 (21-bit grinding): smallest-nonce PoW must match the oracle."""
+    p = T.training_prover(1, Z.ProofOptions.reference())
+    trace = p.build_trace()
+    _prove_both(gpu_ctx, oracle, p.describe(trace), trace)
+
+
+def test_training_synthetic_8192(gpu_ctx, oracle):
+    """bs=50-sized trace (the largest the reference CLI reaches, src/main.rs:77): two-pass NTT, 2^17-row LDE."""
+    n = 8192
+    data = T.random_felts(240 * n, 0x5EED0400).reshape(240, n, 2)
+    air = T.synthetic_training_air(n, T.options(), data)
+    _prove_both(gpu_ctx, oracle, air, Z.TraceTable(data))
+
+
+def test_python_prover_surface(gpu_ctx, oracle):
+    """`prover.prove(trace)` as main.rs drives it, verified by the oracle's restatement of winterfell::verify."""
+    p = T.aggregation_prover(16, T.options())
+    trace = p.build_trace()
+    proof = p.prove(trace)
+    oracle.verify(p.describe(trace), proof.to_bytes())
+    assert proof.transcript.n_positions > 0 and len(proof) == len(proof.to_bytes())
+
+
+def test_invalid_inputs_rejected(gpu_ctx):
+    """tests/integration_tests.rs:201-230 expects a panic on mismatched batch sizes; the C ABI returns ZKB_ERR_INVALID."""
+    with pytest.raises(AssertionError):
+        Z.TrainingUpdateProver(T.options(), [[0] * 9] * 6, [0] * 6, [[0] * 9] * 6, [0] * 6, [[0] * 9], [[0] * 9], [[0] * 6], 1, 1, 2)
+    p = T.mimc_prover(2, 64, T.options(blowup=8))
+    trace = p.build_trace()
+    air = p.describe(trace)
+    bad = dict(air)
+    bad["options"] = dict(air["options"], blowup=4)  # below the degree-7 constraint blowup
+    data = np.ascontiguousarray(trace.data)
+    with pytest.raises(L.ZkbError) as e:
+        gpu_ctx.prove_host(bad, data.ctypes.data)
+    assert e.value.status == -1
+    bad = dict(air, assertions=[(5, 0, 1)])  # column out of range
+    with pytest.raises(L.ZkbError):
+        gpu_ctx.prove_host(bad, data.ctypes.data)
+
+
+def test_staged_api_matches_one_shot(gpu_ctx, oracle):
+    """The staged surface (TraceLde / ConstraintEvaluator / ConstraintCommitment + DEEP/FRI stages) reproduces the oracle transcript."""
+    p = T.aggregation_prover(16, T.options())
+    trace = p.build_trace()
+    air = p.describe(trace)
+    _, ts, _ = oracle.prove(air, trace.to_bytes())
+    lib, h = gpu_ctx.lib, gpu_ctx.handle
+    d = L.make_desc(air)
+    data = np.ascontiguousarray(trace.data)
+    w, n = trace.width(), trace.length()
+    cols = (C.c_void_p * w)(*[data.ctypes.data + j * n * 16 for j in range(w)])
+    root = C.create_string_buffer(32)
+    gpu_ctx.check(lib.zkb_begin(h, C.byref(d)))
+    gpu_ctx.check(lib.zkb_trace_commit(h, cols, root))
+    assert root.raw == bytes(ts.trace_root)
+    # TraceLde::read_main_trace_frame_into
+    cur, nxt = C.create_string_buffer(16 * w), C.create_string_buffer(16 * w)
+    gpu_ctx.check(lib.zkb_trace_read_frame(h, C.c_uint64(0), cur, nxt))
+    _, lde, _ = oracle.trace_commit(trace.to_bytes(), n, w, 16, want_lde=True)
+    assert cur.raw == lde[:16 * w] and nxt.raw == lde[16 * 16 * w:17 * 16 * w]
+    gpu_ctx.check(lib.zkb_constraints_eval(h, bytes(ts.constraint_alpha), None))
+    gpu_ctx.check(lib.zkb_constraints_commit(h, root))
+    assert root.raw == bytes(ts.constraint_root)
+    # out-of-order call is refused
+    assert lib.zkb_deep_compose(h, bytes(ts.deep_alpha)) == -3
+    gpu_ctx.check(lib.zkb_ood_eval(h, bytes(ts.z), None, None, None))
+    gpu_ctx.check(lib.zkb_deep_compose(h, bytes(ts.deep_alpha)))
+    nl = C.c_uint32()
+    gpu_ctx.check(lib.zkb_fri_num_layers(h, C.byref(nl)))
+    assert nl.value == ts.n_fri_layers
+    for l in range(nl.value):
+        gpu_ctx.check(lib.zkb_fri_commit_layer(h, root))
+        assert root.raw == bytes(ts.fri_roots[l])
+        gpu_ctx.check(lib.zkb_fri_fold(h, bytes(ts.fri_alphas[l])))
+    rem, cnt = C.create_string_buffer(16 * 64), C.c_uint64()
+    gpu_ctx.check(lib.zkb_fri_remainder(h, rem, C.byref(cnt), root))
+    assert root.raw == bytes(ts.remainder_commitment)

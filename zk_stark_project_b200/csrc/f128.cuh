@@ -1,0 +1,208 @@
+// f128 device arithmetic for sm_100a: the STARK base field of the reference
+// (winter-math f128::BaseElement, selected at /root/reference src/training/prover.rs:9,
+// src/aggregation/prover.rs:12): p = 2^128 - 45*2^40 + 1, canonical little-endian u128.
+//
+// Elements are four 32-bit limbs in registers (one uint4 / 128-bit access in memory).  A product is
+// 16 IMAD.WIDE on the FMA pipe (even/odd carry chains) folded twice with 2^128 = C (mod p),
+// C = 45*2^40 - 1 = {0xFFFFFFFF, 0x2CFF}; the fold is itself done with multiply-accumulate chains so
+// the work is split between the FMA and ALU pipes instead of piling onto the ALU pipe.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace zkb {
+
+struct __align__(16) fe {
+    uint32_t x[4];
+};
+
+#define ZKB_C0 0xFFFFFFFFu
+#define ZKB_C1 0x00002CFFu
+// p limbs: {0x00000001, 0xFFFFD300, 0xFFFFFFFF, 0xFFFFFFFF}
+
+__device__ __forceinline__ fe fe_zero() { fe r; r.x[0] = r.x[1] = r.x[2] = r.x[3] = 0; return r; }
+__device__ __forceinline__ fe fe_one() { fe r; r.x[0] = 1; r.x[1] = r.x[2] = r.x[3] = 0; return r; }
+__device__ __forceinline__ fe fe_from_u64(uint64_t v) { fe r; r.x[0] = (uint32_t)v; r.x[1] = (uint32_t)(v >> 32); r.x[2] = r.x[3] = 0; return r; }
+__device__ __forceinline__ bool fe_is_zero(const fe& a) { return (a.x[0] | a.x[1] | a.x[2] | a.x[3]) == 0; }
+__device__ __forceinline__ bool fe_eq(const fe& a, const fe& b) {
+    return ((a.x[0] ^ b.x[0]) | (a.x[1] ^ b.x[1]) | (a.x[2] ^ b.x[2]) | (a.x[3] ^ b.x[3])) == 0;
+}
+
+__device__ __forceinline__ fe fe_load(const fe* p) {
+    uint4 v = *reinterpret_cast<const uint4*>(p);
+    fe r; r.x[0] = v.x; r.x[1] = v.y; r.x[2] = v.z; r.x[3] = v.w; return r;
+}
+__device__ __forceinline__ fe fe_ldg(const fe* p) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    fe r; r.x[0] = v.x; r.x[1] = v.y; r.x[2] = v.z; r.x[3] = v.w; return r;
+}
+__device__ __forceinline__ void fe_store(fe* p, const fe& a) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(a.x[0], a.x[1], a.x[2], a.x[3]);
+}
+
+// r + C with carry-out  <=>  r >= p; select the wrapped value then (canonicalisation step)
+__device__ __forceinline__ fe fe_canon(const fe& a, uint32_t carry_in) {
+    uint32_t t0, t1, t2, t3, cy;
+    asm("add.cc.u32 %0, %5, %9;\n\t"
+        "addc.cc.u32 %1, %6, %10;\n\t"
+        "addc.cc.u32 %2, %7, 0;\n\t"
+        "addc.cc.u32 %3, %8, 0;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3), "=r"(cy)
+        : "r"(a.x[0]), "r"(a.x[1]), "r"(a.x[2]), "r"(a.x[3]), "r"(ZKB_C0), "r"(ZKB_C1));
+    bool sel = (cy | carry_in) != 0;
+    fe r;
+    r.x[0] = sel ? t0 : a.x[0]; r.x[1] = sel ? t1 : a.x[1]; r.x[2] = sel ? t2 : a.x[2]; r.x[3] = sel ? t3 : a.x[3];
+    return r;
+}
+
+__device__ __forceinline__ fe fe_add(const fe& a, const fe& b) {
+    fe s; uint32_t cy;
+    asm("add.cc.u32 %0, %5, %9;\n\t"
+        "addc.cc.u32 %1, %6, %10;\n\t"
+        "addc.cc.u32 %2, %7, %11;\n\t"
+        "addc.cc.u32 %3, %8, %12;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "=r"(s.x[0]), "=r"(s.x[1]), "=r"(s.x[2]), "=r"(s.x[3]), "=r"(cy)
+        : "r"(a.x[0]), "r"(a.x[1]), "r"(a.x[2]), "r"(a.x[3]), "r"(b.x[0]), "r"(b.x[1]), "r"(b.x[2]), "r"(b.x[3]));
+    return fe_canon(s, cy);
+}
+
+__device__ __forceinline__ fe fe_sub(const fe& a, const fe& b) {
+    fe d; uint32_t bw;
+    asm("sub.cc.u32 %0, %5, %9;\n\t"
+        "subc.cc.u32 %1, %6, %10;\n\t"
+        "subc.cc.u32 %2, %7, %11;\n\t"
+        "subc.cc.u32 %3, %8, %12;\n\t"
+        "subc.u32 %4, 0, 0;"  // 0 or 0xFFFFFFFF
+        : "=r"(d.x[0]), "=r"(d.x[1]), "=r"(d.x[2]), "=r"(d.x[3]), "=r"(bw)
+        : "r"(a.x[0]), "r"(a.x[1]), "r"(a.x[2]), "r"(a.x[3]), "r"(b.x[0]), "r"(b.x[1]), "r"(b.x[2]), "r"(b.x[3]));
+    // on borrow add p, i.e. subtract C (mod 2^128)
+    fe r;
+    asm("sub.cc.u32 %0, %4, %8;\n\t"
+        "subc.cc.u32 %1, %5, %9;\n\t"
+        "subc.cc.u32 %2, %6, 0;\n\t"
+        "subc.u32 %3, %7, 0;"
+        : "=r"(r.x[0]), "=r"(r.x[1]), "=r"(r.x[2]), "=r"(r.x[3])
+        : "r"(d.x[0]), "r"(d.x[1]), "r"(d.x[2]), "r"(d.x[3]), "r"(bw & ZKB_C0), "r"(bw & ZKB_C1));
+    return r;
+}
+__device__ __forceinline__ fe fe_neg(const fe& a) { return fe_sub(fe_zero(), a); }
+
+// 128x128 -> 256-bit product, even/odd accumulation so every mad.lo/mad.hi pair is one IMAD.WIDE
+__device__ __forceinline__ void mul_wide(const fe& a, const fe& b, uint32_t r[8]) {
+    uint32_t e0, e1, e2, e3, e4, e5, e6, e7, o0, o1, o2, o3, o4, o5, o6;
+    const uint32_t a0 = a.x[0], a1 = a.x[1], a2 = a.x[2], a3 = a.x[3];
+    const uint32_t b0 = b.x[0], b1 = b.x[1], b2 = b.x[2], b3 = b.x[3];
+    asm("{\n\t"
+        // row b0
+        "mul.lo.u32 %0, %15, %19;\n\t mul.hi.u32 %1, %15, %19;\n\t"
+        "mul.lo.u32 %2, %17, %19;\n\t mul.hi.u32 %3, %17, %19;\n\t"
+        "mul.lo.u32 %8, %16, %19;\n\t mul.hi.u32 %9, %16, %19;\n\t"
+        "mul.lo.u32 %10, %18, %19;\n\t mul.hi.u32 %11, %18, %19;\n\t"
+        // row b1: a0,a2 -> odd ; a1,a3 -> even
+        "mad.lo.cc.u32 %8, %15, %20, %8;\n\t madc.hi.cc.u32 %9, %15, %20, %9;\n\t"
+        "madc.lo.cc.u32 %10, %17, %20, %10;\n\t madc.hi.cc.u32 %11, %17, %20, %11;\n\t"
+        "addc.u32 %12, 0, 0;\n\t"
+        "mad.lo.cc.u32 %2, %16, %20, %2;\n\t madc.hi.cc.u32 %3, %16, %20, %3;\n\t"
+        "madc.lo.cc.u32 %4, %18, %20, 0;\n\t madc.hi.u32 %5, %18, %20, 0;\n\t"
+        // row b2: a0,a2 -> even ; a1,a3 -> odd
+        "mad.lo.cc.u32 %2, %15, %21, %2;\n\t madc.hi.cc.u32 %3, %15, %21, %3;\n\t"
+        "madc.lo.cc.u32 %4, %17, %21, %4;\n\t madc.hi.cc.u32 %5, %17, %21, %5;\n\t"
+        "addc.u32 %6, 0, 0;\n\t"
+        "mad.lo.cc.u32 %10, %16, %21, %10;\n\t madc.hi.cc.u32 %11, %16, %21, %11;\n\t"
+        "madc.lo.cc.u32 %12, %18, %21, %12;\n\t madc.hi.cc.u32 %13, %18, %21, 0;\n\t"
+        "addc.u32 %14, 0, 0;\n\t"
+        // row b3: a0,a2 -> odd ; a1,a3 -> even
+        "mad.lo.cc.u32 %10, %15, %22, %10;\n\t madc.hi.cc.u32 %11, %15, %22, %11;\n\t"
+        "madc.lo.cc.u32 %12, %17, %22, %12;\n\t madc.hi.cc.u32 %13, %17, %22, %13;\n\t"
+        "addc.u32 %14, %14, 0;\n\t"
+        "mad.lo.cc.u32 %4, %16, %22, %4;\n\t madc.hi.cc.u32 %5, %16, %22, %5;\n\t"
+        "madc.lo.cc.u32 %6, %18, %22, %6;\n\t madc.hi.u32 %7, %18, %22, 0;\n\t"
+        "}"
+        : "=&r"(e0), "=&r"(e1), "=&r"(e2), "=&r"(e3), "=&r"(e4), "=&r"(e5), "=&r"(e6), "=&r"(e7),
+          "=&r"(o0), "=&r"(o1), "=&r"(o2), "=&r"(o3), "=&r"(o4), "=&r"(o5), "=&r"(o6)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3));
+    // r = even + (odd << 32)
+    r[0] = e0;
+    asm("add.cc.u32 %0, %7, %14;\n\t"
+        "addc.cc.u32 %1, %8, %15;\n\t"
+        "addc.cc.u32 %2, %9, %16;\n\t"
+        "addc.cc.u32 %3, %10, %17;\n\t"
+        "addc.cc.u32 %4, %11, %18;\n\t"
+        "addc.cc.u32 %5, %12, %19;\n\t"
+        "addc.u32 %6, %13, %20;"
+        : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(e1), "r"(e2), "r"(e3), "r"(e4), "r"(e5), "r"(e6), "r"(e7),
+          "r"(o0), "r"(o1), "r"(o2), "r"(o3), "r"(o4), "r"(o5), "r"(o6));
+}
+
+// lo(128) + hi(128) * 2^128  ->  canonical element
+__device__ __forceinline__ fe fe_reduce256(const uint32_t v[8]) {
+    uint32_t r0 = v[0], r1 = v[1], r2 = v[2], r3 = v[3], r4, r5;
+    uint32_t o0, o1, o2, o3, o4;
+    const uint32_t h0 = v[4], h1 = v[5], h2 = v[6], h3 = v[7];
+    const uint32_t c0 = ZKB_C0, c1 = ZKB_C1;
+    // first fold: (r0..r5) = lo + hi * C
+    asm("{\n\t"
+        "mad.lo.cc.u32 %0, %11, %15, %0;\n\t madc.hi.cc.u32 %1, %11, %15, %1;\n\t"
+        "madc.lo.cc.u32 %2, %13, %15, %2;\n\t madc.hi.cc.u32 %3, %13, %15, %3;\n\t"
+        "addc.u32 %4, 0, 0;\n\t"
+        "mad.lo.cc.u32 %2, %12, %16, %2;\n\t madc.hi.cc.u32 %3, %12, %16, %3;\n\t"
+        "madc.lo.cc.u32 %4, %14, %16, %4;\n\t madc.hi.u32 %5, %14, %16, 0;\n\t"
+        "mul.lo.u32 %6, %12, %15;\n\t mul.hi.u32 %7, %12, %15;\n\t"
+        "mul.lo.u32 %8, %14, %15;\n\t mul.hi.u32 %9, %14, %15;\n\t"
+        "mad.lo.cc.u32 %6, %11, %16, %6;\n\t madc.hi.cc.u32 %7, %11, %16, %7;\n\t"
+        "madc.lo.cc.u32 %8, %13, %16, %8;\n\t madc.hi.cc.u32 %9, %13, %16, %9;\n\t"
+        "addc.u32 %10, 0, 0;\n\t"
+        "add.cc.u32 %1, %1, %6;\n\t addc.cc.u32 %2, %2, %7;\n\t addc.cc.u32 %3, %3, %8;\n\t"
+        "addc.cc.u32 %4, %4, %9;\n\t addc.u32 %5, %5, %10;\n\t"
+        "}"
+        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "=&r"(r4), "=&r"(r5),
+          "=&r"(o0), "=&r"(o1), "=&r"(o2), "=&r"(o3), "=&r"(o4)
+        : "r"(h0), "r"(h1), "r"(h2), "r"(h3), "r"(c0), "r"(c1));
+    // second fold: top = r5:r4 < 2^46;  r += top * C, counting wraps of 2^128 (at most one)
+    uint32_t cy;
+    asm("{\n\t"
+        ".reg .u32 t;\n\t"
+        "mul.lo.u32 t, %6, %8;\n\t"  // t1*c1 < 2^28, weight 2^64
+        "mad.lo.cc.u32 %0, %5, %7, %0;\n\t madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "addc.cc.u32 %2, %2, t;\n\t addc.cc.u32 %3, %3, 0;\n\t addc.u32 %4, 0, 0;\n\t"
+        "mad.lo.cc.u32 %1, %5, %8, %1;\n\t madc.hi.cc.u32 %2, %5, %8, %2;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t addc.u32 %4, %4, 0;\n\t"
+        "mad.lo.cc.u32 %1, %6, %7, %1;\n\t madc.hi.cc.u32 %2, %6, %7, %2;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t addc.u32 %4, %4, 0;\n\t"
+        "}"
+        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "=&r"(cy)
+        : "r"(r4), "r"(r5), "r"(c0), "r"(c1));
+    // a wrap (cy) and "value >= p" are both fixed by adding C modulo 2^128
+    fe out; out.x[0] = r0; out.x[1] = r1; out.x[2] = r2; out.x[3] = r3;
+    return fe_canon(out, cy);
+}
+
+__device__ __forceinline__ fe fe_mul(const fe& a, const fe& b) {
+    uint32_t w[8];
+    mul_wide(a, b, w);
+    return fe_reduce256(w);
+}
+__device__ __forceinline__ fe fe_sqr(const fe& a) { return fe_mul(a, a); }
+
+// a^e for a 128-bit exponent given as limbs (used for inversion and small fixed powers)
+__device__ __forceinline__ fe fe_pow_u64(fe b, uint64_t e) {
+    fe r = fe_one();
+    while (e) { if (e & 1) r = fe_mul(r, b); b = fe_sqr(b); e >>= 1; }
+    return r;
+}
+// a^(p-2); inv(0) = 0 as in winter-math
+__device__ __noinline__ fe fe_inv(const fe& a) {
+    // p - 2 = 0xFFFFFFFF_FFFFFFFF_FFFFD2FF_FFFFFFFF
+    const uint32_t e[4] = {0xFFFFFFFFu, 0xFFFFD2FFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    fe r = fe_one();
+    for (int i = 127; i >= 0; i--) {
+        r = fe_sqr(r);
+        if ((e[i >> 5] >> (i & 31)) & 1) r = fe_mul(r, a);
+    }
+    return r;
+}
+
+}  // namespace zkb

@@ -1,0 +1,556 @@
+// CUDA kernels of the proving hot path (sm_100a).  Stage numbering K1..K11 follows SURVEY.md §2.4;
+// each kernel names the Winterfell stage it replaces and the reference line that selects that stage.
+//
+// Data layouts in HBM (all elements 16 B little-endian canonical f128):
+//   trace      column-major [w][n]                    as handed over by the caller (TraceTable columns)
+//   polys      row-major    [n][w]  (coefficient m major, column j minor)
+//   LDE        "panel" layout: rows that the last NTT pass of one coset produces together form a panel
+//              of P = 2^log_p rows, stored column-major inside the panel:
+//                 row r = i*beta + k  (i = trace-domain index, k = coset),  T = n/P,
+//                 panel = k*T + (i mod T),  slot = i div T,
+//                 addr(r, j) = ((panel*w + j) << log_p) + slot
+//              so that a kernel with one thread per row (hashing, constraint evaluation, DEEP) reads
+//              column j of 32 consecutive slots as one coalesced 512-byte request.
+#pragma once
+#include "f128.cuh"
+#include "blake3.cuh"
+
+namespace zkb {
+
+// two-level power table: base^e = lo[e & (2^l1 - 1)] * hi[e >> l1]
+struct PowTab {
+    const fe* lo;
+    const fe* hi;
+    uint32_t l1;
+};
+__device__ __forceinline__ fe powtab(const PowTab& t, uint32_t e) {
+    fe a = fe_ldg(t.lo + (e & ((1u << t.l1) - 1u)));
+    fe b = fe_ldg(t.hi + (e >> t.l1));
+    return fe_mul(a, b);
+}
+
+struct LdeMat {
+    fe* data;
+    uint32_t log_n, log_beta, w, log_p;
+};
+__device__ __forceinline__ size_t lde_addr(const LdeMat& m, uint32_t k, uint32_t i, uint32_t j) {
+    const uint32_t lt = m.log_n - m.log_p;
+    const uint32_t t_low = i & ((1u << lt) - 1u), slot = i >> lt;
+    const size_t panel = ((size_t)k << lt) + t_low;
+    return ((panel * m.w + j) << m.log_p) + slot;
+}
+
+// ------------------------------------------------------------------------------------------------
+// transpose: column-major [w][n] -> row-major [n][w]   (first step of K1)
+__global__ void k_transpose_cols(const fe* __restrict__ in, fe* __restrict__ out, uint32_t n, uint32_t w) {
+    __shared__ uint4 tile[32][33];
+    const uint32_t i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    for (uint32_t jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+        uint32_t j = j0 + jj, i = i0 + threadIdx.x;
+        if (j < w && i < n) tile[jj][threadIdx.x] = reinterpret_cast<const uint4*>(in)[(size_t)j * n + i];
+    }
+    __syncthreads();
+    for (uint32_t ii = threadIdx.y; ii < 32; ii += blockDim.y) {
+        uint32_t i = i0 + ii, j = j0 + threadIdx.x;
+        if (j < w && i < n) reinterpret_cast<uint4*>(out)[(size_t)i * w + j] = tile[threadIdx.x][ii];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1/K2/K6/K8: one pass of a column-batched radix-2 DIT NTT over layers (a, b].
+//
+// Mathematics (Winterfell fft::interpolate_poly / evaluate_poly_with_offset, reached through
+// DefaultTraceLde::new at src/training/prover.rs:280 and DefaultConstraintCommitment::new at :299):
+//   A_l[u][t] = sum_{m' < 2^l} c[u + (n/2^l) m'] * s_l^{m'} * w_{2^l}^{m' t},   s_l = s^{n/2^l}
+//   A_l[u][t'], A_l[u][t' + 2^{l-1}] = A_{l-1}[u][t'] +- (s_l w_{2^l}^{t'}) * A_{l-1}[u + n/2^l][t']
+// with s = 3*w_N^k for coset k of the LDE (the coset shift is folded into the twiddles, so the LDE costs
+// exactly (n/2) log n multiplications per coset and column), s = 1 and inverse roots for interpolation.
+// Between passes the array holds A_b as  index = u*2^b + t  (row-major [index][column]).
+// A tile = S = 2^(b-a) rows (u = u0 + (n/2^b) v, fixed t_low) x cj columns staged in shared memory;
+// its S-1 twiddles are generated once per tile and shared by all columns of the batch.
+struct NttPass {
+    const fe* in;
+    fe* out;
+    uint32_t log_n, a, b;          // transform size, layer range
+    uint32_t w_in, w_out;          // row widths of the in / out matrices (elements)
+    uint32_t col0_in, col0_out, ncols, cj;
+    uint32_t n_cosets, coset0;     // cosets k = coset0 + kk; ignored when `coset` == 0
+    uint64_t in_coset_stride, out_coset_stride;  // elements between consecutive cosets (0 = shared input)
+    uint32_t coset;                // 1: s = 3*w_N^k (forward roots); 0: s = 1
+    uint32_t inverse;              // 1: inverse roots (interpolation)
+    uint32_t log_tab;              // root table covers <w_{2^log_tab}>
+    uint32_t log_lde;              // log2(n * beta) for coset transforms
+    uint32_t out_panel;            // final pass of an LDE: write the panel layout
+    uint32_t do_scale;             // multiply outputs by `scale` (1/n for interpolation)
+    fe scale;
+    PowTab roots;                  // w_{2^log_tab}^e
+    const fe* pow3;                // pow3[l] = 3^(n >> l), l = 0..log_n
+};
+
+__device__ __forceinline__ uint32_t bitrev(uint32_t v, uint32_t bits) { return bits == 0 ? 0u : (__brev(v) >> (32 - bits)); }
+
+__global__ void __launch_bounds__(256) k_ntt_pass(const NttPass p) {
+    extern __shared__ uint4 smem_raw[];
+    fe* sm = reinterpret_cast<fe*>(smem_raw);
+    const uint32_t logS = p.b - p.a, S = 1u << logS, cj = p.cj;
+    const uint32_t rs = cj + (cj > 1 ? 1u : 0u);  // padded row stride: conflict-free column reads
+    fe* tw = sm + (size_t)S * rs;
+
+    // tile coordinates: column tile fastest, then coset (so one input tile is reused out of L2), then (t_low, u0)
+    const uint32_t n_ct = (p.ncols + cj - 1) / cj;
+    uint32_t id = blockIdx.x;
+    const uint32_t ct = id % n_ct; id /= n_ct;
+    const uint32_t kk = id % p.n_cosets; id /= p.n_cosets;
+    const uint32_t t_low = id & ((1u << p.a) - 1u);
+    const uint32_t u0 = id >> p.a;
+    const uint32_t k = p.coset0 + kk;
+    const fe* in = p.in + (size_t)kk * p.in_coset_stride;
+    fe* out = p.out + (size_t)kk * p.out_coset_stride;
+    const uint32_t tab_mask = (1u << p.log_tab) - 1u;
+
+    // twiddles: tw[2^(lam-1) - 1 + th] = s_l * w_{2^l}^{t_low} * w_{2^lam}^{th},  l = a + lam
+    for (uint32_t q = threadIdx.x; q + 1 < S; q += blockDim.x) {
+        const uint32_t lam = 32 - __clz(q + 1);      // 1..logS
+        const uint32_t th = q + 1 - (1u << (lam - 1));
+        const uint32_t l = p.a + lam;
+        // exponent in units of w_{2^log_tab}
+        uint32_t e = (t_low << (p.log_tab - l)) + (th << (p.log_tab - lam));
+        if (p.coset) e += (k << (p.log_n - l)) << (p.log_tab - p.log_lde);
+        e &= tab_mask;
+        if (p.inverse) e = (0u - e) & tab_mask;
+        fe t = powtab(p.roots, e);
+        if (p.coset) t = fe_mul(t, fe_ldg(p.pow3 + l));
+        tw[q] = t;
+    }
+    // load: row v of the tile is input row (u0 + (n/2^b) v) * 2^a + t_low; store bit-reversed
+    const uint32_t c_base = ct * cj;
+    const uint32_t E = S * cj;
+    for (uint32_t idx = threadIdx.x; idx < E; idx += blockDim.x) {
+        const uint32_t v = idx / cj, jj = idx - v * cj;
+        const size_t row = (((size_t)u0 + ((size_t)v << (p.log_n - p.b))) << p.a) + t_low;
+        fe x = fe_zero();
+        if (c_base + jj < p.ncols) x = fe_load(in + row * p.w_in + p.col0_in + c_base + jj);
+        sm[bitrev(v, logS) * rs + jj] = x;
+    }
+    __syncthreads();
+    // butterflies
+    const uint32_t nb = (S >> 1) * cj;
+    for (uint32_t lam = 1; lam <= logS; lam++) {
+        const uint32_t half = 1u << (lam - 1);
+        for (uint32_t bidx = threadIdx.x; bidx < nb; bidx += blockDim.x) {
+            const uint32_t q = bidx / cj, jj = bidx - q * cj;
+            const uint32_t th = q & (half - 1u);
+            const uint32_t p0 = ((q >> (lam - 1)) << lam) + th;
+            fe* x0 = sm + p0 * rs + jj;
+            fe* x1 = x0 + half * rs;
+            const fe u = *x0;
+            const fe v = fe_mul(*x1, tw[half - 1u + th]);
+            *x0 = fe_add(u, v);
+            *x1 = fe_sub(u, v);
+        }
+        __syncthreads();
+    }
+    // store
+    if (p.out_panel) {
+        // panel = k*2^a + t_low, slot = t_high; consecutive threads write consecutive slots of one column
+        const size_t panel = ((size_t)k << p.a) + t_low;
+        for (uint32_t idx = threadIdx.x; idx < E; idx += blockDim.x) {
+            const uint32_t jj = idx >> logS, th = idx & (S - 1u);
+            if (c_base + jj < p.ncols) {
+                fe x = sm[th * rs + jj];
+                fe_store(p.out + ((panel * p.w_out + p.col0_out + c_base + jj) << logS) + th, x);
+            }
+        }
+    } else {
+        for (uint32_t idx = threadIdx.x; idx < E; idx += blockDim.x) {
+            const uint32_t th = idx / cj, jj = idx - th * cj;
+            if (c_base + jj < p.ncols) {
+                fe x = sm[th * rs + jj];
+                if (p.do_scale) x = fe_mul(x, p.scale);
+                const size_t row = ((size_t)u0 << p.b) + t_low + ((size_t)th << p.a);
+                fe_store(out + row * p.w_out + p.col0_out + c_base + jj, x);
+            }
+        }
+    }
+}
+
+// x[m] *= scale * base^m   (interpolate_poly_with_offset: base = 1/offset)
+__global__ void k_scale_pow(fe* x, uint64_t n, PowTab base, fe scale) {
+    uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    fe f = fe_mul(powtab(base, (uint32_t)m), scale);
+    fe_store(x + m, fe_mul(fe_load(x + m), f));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: leaf = Blake3_256::hash_elements(LDE row)  (RowMatrix::commit_to_rows; src/training/prover.rs:225,280)
+// one thread per LDE row, enumerated (panel, slot) so that a warp reads 32 consecutive slots per column
+__global__ void __launch_bounds__(128) k_hash_lde_rows(const LdeMat m, uint32_t* __restrict__ leaves) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t log_N = m.log_n + m.log_beta;
+    if (gid >> log_N) return;
+    const uint32_t lt = m.log_n - m.log_p;
+    const uint32_t slot = (uint32_t)gid & ((1u << m.log_p) - 1u);
+    const uint32_t panel = (uint32_t)(gid >> m.log_p);
+    const uint32_t k = panel >> lt, t_low = panel & ((1u << lt) - 1u);
+    const uint32_t i = t_low + (slot << lt);
+    const uint64_t r = ((uint64_t)i << m.log_beta) + k;
+    uint32_t d[8];
+    b3_hash_elems(m.data + (((size_t)panel * m.w) << m.log_p) + slot, (size_t)1 << m.log_p, m.w, d);
+    uint4* o = reinterpret_cast<uint4*>(leaves + r * 8);
+    o[0] = make_uint4(d[0], d[1], d[2], d[3]);
+    o[1] = make_uint4(d[4], d[5], d[6], d[7]);
+}
+
+// FRI layer rows: leaf_i = hash_elements([e[i + j*rows]]_{j<F})   (winter-fri build_layer / transpose_slice)
+__global__ void __launch_bounds__(128) k_hash_strided_rows(const fe* __restrict__ e, uint64_t rows, uint32_t count, uint32_t* __restrict__ leaves) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    uint32_t d[8];
+    b3_hash_elems(e + i, rows, count, d);
+    uint4* o = reinterpret_cast<uint4*>(leaves + i * 8);
+    o[0] = make_uint4(d[0], d[1], d[2], d[3]);
+    o[1] = make_uint4(d[4], d[5], d[6], d[7]);
+}
+
+// K4: one level of MerkleTree::new (build_merkle_nodes): dst[i] = merge(src[2i], src[2i+1])
+__global__ void __launch_bounds__(256) k_merkle_level(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint64_t count) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint4* s = reinterpret_cast<const uint4*>(src + i * 16);
+    uint32_t m[16], cv[8];
+    uint4 a = s[0], b = s[1], c = s[2], d = s[3];
+    m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+    m[8] = c.x; m[9] = c.y; m[10] = c.z; m[11] = c.w; m[12] = d.x; m[13] = d.y; m[14] = d.z; m[15] = d.w;
+    b3_iv(cv);
+    b3_compress(cv, m, 0, 64, B3_CHUNK_START | B3_CHUNK_END | B3_ROOT);
+    uint4* o = reinterpret_cast<uint4*>(dst + i * 8);
+    o[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+    o[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: DefaultConstraintEvaluator::evaluate (src/training/prover.rs:283-290) fused with
+// ConstraintEvaluationTable::combine: one thread per constraint-evaluation-domain point.
+enum { ZKB_AIR_TRAINING = 1, ZKB_AIR_AGGREGATION = 2, ZKB_AIR_MIMC = 3 };
+#define ZKB_MAX_GROUPS 8
+struct EvalParams {
+    LdeMat lde;
+    uint32_t air_id, log_ce;      // ce blowup = 2^log_ce
+    uint32_t n_trans;             // number of transition constraints
+    const fe* tcoef;              // transition coefficients (alpha^0 ..)
+    uint32_t n_groups;
+    uint32_t g_off[ZKB_MAX_GROUPS + 1];  // assertion ranges per boundary group
+    fe g_point[ZKB_MAX_GROUPS];   // g^step of the group's divisor (x - g^step)
+    const uint32_t* a_col;        // per assertion: column, value, coefficient
+    const fe* a_val;
+    const fe* a_coef;
+    const fe* zinv;               // 1/(x^n - 1) for the 2^log_ce cosets used
+    fe g_last;                    // g^(n-1): transition exemption point
+    fe k;                         // aggregation scaling factor (src/aggregation/air.rs:108)
+    const fe* periodic;           // MiMC: round-constant column over the ce domain, length per_len
+    uint32_t per_mask;
+    PowTab roots; uint32_t log_tab;
+    fe* out;                      // composition trace, natural ce-domain order
+};
+
+__global__ void __launch_bounds__(128) k_eval_constraints(const EvalParams p) {
+    const LdeMat& m = p.lde;
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >> (m.log_n + p.log_ce)) return;
+    const uint32_t lt = m.log_n - m.log_p;
+    const uint32_t slot = (uint32_t)gid & ((1u << m.log_p) - 1u);
+    const uint32_t t_low = (uint32_t)(gid >> m.log_p) & ((1u << lt) - 1u);
+    const uint32_t kc = (uint32_t)(gid >> m.log_n);
+    const uint32_t k = kc << (m.log_beta - p.log_ce);
+    const uint32_t i = t_low + (slot << lt);
+    const uint32_t i1 = (i + 1u) & ((1u << m.log_n) - 1u);  // frame.next = row + blowup (mod N)
+    const uint32_t ci = (i << p.log_ce) + kc;
+    const uint32_t log_N = m.log_n + m.log_beta;
+    const uint32_t r = (i << m.log_beta) + k;
+    const fe* cur = m.data + lde_addr(m, k, i, 0);
+    const fe* nxt = m.data + lde_addr(m, k, i1, 0);
+    const size_t cs = (size_t)1 << m.log_p;  // column stride
+
+    // x = 3 * w_N^r
+    fe x = powtab(p.roots, r << (p.log_tab - log_N));
+    { fe x2 = fe_add(x, x); x = fe_add(x2, x); }
+
+    // transition constraints, merged with their coefficients
+    fe t = fe_zero();
+    if (p.air_id == ZKB_AIR_AGGREGATION) {
+        const uint32_t d = p.n_trans;
+        for (uint32_t c = 0; c < d; c++) {
+            fe dn = fe_sub(fe_load(nxt + c * cs), fe_load(cur + c * cs));
+            fe ev = fe_sub(fe_mul(p.k, dn), fe_load(nxt + (size_t)(c + d) * cs));
+            t = fe_add(t, fe_mul(fe_ldg(p.tcoef + c), ev));
+        }
+    } else if (p.air_id == ZKB_AIR_MIMC) {
+        const fe rc = fe_ldg(p.periodic + (ci & p.per_mask));
+        for (uint32_t c = 0; c < p.n_trans; c++) {
+            fe a1 = fe_add(fe_load(cur + c * cs), rc);
+            fe a2 = fe_sqr(a1), a4 = fe_sqr(a2), a6 = fe_mul(a4, a2), a7 = fe_mul(a6, a1);
+            fe ev = fe_sub(fe_load(nxt + c * cs), a7);
+            t = fe_add(t, fe_mul(fe_ldg(p.tcoef + c), ev));
+        }
+    }  // TRAINING: every transition evaluation is zero (src/training/air.rs:274-278, src/helper.rs:141-146)
+
+    // boundary groups: sum coef * (cur[col] - value), divided by (x - g^step)
+    fe num[ZKB_MAX_GROUPS], den[ZKB_MAX_GROUPS], pre[ZKB_MAX_GROUPS];
+    fe acc = fe_one();
+    for (uint32_t g = 0; g < p.n_groups; g++) {
+        fe s = fe_zero();
+        for (uint32_t a = p.g_off[g]; a < p.g_off[g + 1]; a++) {
+            fe v = fe_sub(fe_load(cur + (size_t)__ldg(p.a_col + a) * cs), fe_ldg(p.a_val + a));
+            s = fe_add(s, fe_mul(fe_ldg(p.a_coef + a), v));
+        }
+        num[g] = s;
+        den[g] = fe_sub(x, p.g_point[g]);
+        pre[g] = acc;
+        acc = fe_mul(acc, den[g]);
+    }
+    fe res = fe_mul(fe_mul(t, fe_sub(x, p.g_last)), fe_ldg(p.zinv + kc));
+    if (p.n_groups) {
+        fe ia = fe_inv(acc);
+        for (int g = (int)p.n_groups - 1; g >= 0; g--) {
+            fe di = fe_mul(ia, pre[g]);
+            ia = fe_mul(ia, den[g]);
+            res = fe_add(res, fe_mul(num[g], di));
+        }
+    }
+    fe_store(p.out + ci, res);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: TracePolyTable::get_ood_frame — T_j(z), T_j(z*g) for all columns (inside Prover::prove)
+// polys row-major [n][w]; block c handles rows [c*R, (c+1)*R), thread j handles column j.
+__global__ void __launch_bounds__(256) k_ood_partial(const fe* __restrict__ polys, uint32_t n, uint32_t w, uint32_t R,
+                                                      fe z, fe zg, const fe* __restrict__ zpow, const fe* __restrict__ zgpow,
+                                                      fe* __restrict__ part_z, fe* __restrict__ part_zg) {
+    const uint32_t j = threadIdx.x, c = blockIdx.x;
+    if (j >= w) return;
+    const uint32_t m0 = c * R;
+    const uint32_t m1 = min(n, m0 + R);
+    fe a = fe_zero(), b = fe_zero();
+    for (uint32_t m = m1; m-- > m0;) {
+        fe v = fe_load(polys + (size_t)m * w + j);
+        a = fe_add(fe_mul(a, z), v);
+        b = fe_add(fe_mul(b, zg), v);
+    }
+    fe_store(part_z + (size_t)c * w + j, fe_mul(a, fe_ldg(zpow + c)));
+    fe_store(part_zg + (size_t)c * w + j, fe_mul(b, fe_ldg(zgpow + c)));
+}
+// out[j] = sum_c part[c][j]
+__global__ void k_col_sum(const fe* __restrict__ part, uint32_t nchunks, uint32_t w, fe* __restrict__ out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= w) return;
+    fe s = fe_zero();
+    for (uint32_t c = 0; c < nchunks; c++) s = fe_add(s, fe_load(part + (size_t)c * w + j));
+    fe_store(out + j, s);
+}
+// CompositionPoly::evaluate_at: H_i(z) for contiguous coefficient columns [c][n]; one block per column chunk
+__global__ void __launch_bounds__(256) k_poly_eval_partial(const fe* __restrict__ coef, uint32_t n, uint32_t Q, fe z, fe zQ,
+                                                           fe* __restrict__ part) {
+    // block handles column blockIdx.y; thread t handles coefficients [t*Q, (t+1)*Q); partial = Horner * z^(t*Q)
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nt = (n + Q - 1) / Q;
+    if (t >= nt) return;
+    const fe* c = coef + (size_t)blockIdx.y * n;
+    const uint32_t m0 = t * Q, m1 = min(n, m0 + Q);
+    fe a = fe_zero();
+    for (uint32_t m = m1; m-- > m0;) a = fe_add(fe_mul(a, z), fe_load(c + m));
+    fe_store(part + (size_t)blockIdx.y * nt + t, fe_mul(a, fe_pow_u64(zQ, t)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8: DEEP composition (winter-prover composer), evaluation form:
+//   A(x) = sum_j gamma_j T_j(x),  B(x) = sum_i gamma'_i H_i(x)
+//   DEEP(x) = (A(x)+B(x) - A(z)-B(z))/(x - z) + (A(x) - A(zg))/(x - zg)
+// which equals Winterfell's coefficient-form quotient at every LDE point.
+// k_deep_combine: AB[m][0] = A coefficients, AB[m][1] = (A+B) coefficients; one warp per coefficient row
+__global__ void __launch_bounds__(256) k_deep_combine(const fe* __restrict__ polys, uint32_t n, uint32_t w,
+                                                      const fe* __restrict__ gamma, const fe* __restrict__ hcoef, uint32_t c,
+                                                      const fe* __restrict__ gamma_h, fe* __restrict__ ab) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    fe s = fe_zero();
+    for (uint32_t j = lane; j < w; j += 32) s = fe_add(s, fe_mul(fe_load(polys + (size_t)warp * w + j), fe_ldg(gamma + j)));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        fe o;
+        o.x[0] = __shfl_down_sync(0xffffffffu, s.x[0], off); o.x[1] = __shfl_down_sync(0xffffffffu, s.x[1], off);
+        o.x[2] = __shfl_down_sync(0xffffffffu, s.x[2], off); o.x[3] = __shfl_down_sync(0xffffffffu, s.x[3], off);
+        s = fe_add(s, o);
+    }
+    if (lane == 0) {
+        fe b = fe_zero();
+        for (uint32_t i = 0; i < c; i++) b = fe_add(b, fe_mul(fe_load(hcoef + (size_t)i * n + warp), fe_ldg(gamma_h + i)));
+        fe_store(ab + (size_t)warp * 2, s);
+        fe_store(ab + (size_t)warp * 2 + 1, fe_add(s, b));
+    }
+}
+// k_deep_eval: each thread handles RPT rows (one Montgomery batch inversion per thread)
+#define ZKB_DEEP_RPT 8
+__global__ void __launch_bounds__(128) k_deep_eval(const LdeMat m, fe z, fe zg, fe az, fe abz, fe azg, PowTab roots, uint32_t log_tab,
+                                                   fe* __restrict__ out) {
+    const uint32_t log_N = m.log_n + m.log_beta;
+    const uint64_t N = (uint64_t)1 << log_N;
+    const uint64_t nthreads = N / ZKB_DEEP_RPT;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= nthreads) return;
+    const uint32_t lt = m.log_n - m.log_p;
+    fe d[2 * ZKB_DEEP_RPT], pre[2 * ZKB_DEEP_RPT], n1[ZKB_DEEP_RPT], n2[ZKB_DEEP_RPT];
+    uint32_t rr[ZKB_DEEP_RPT];
+    fe acc = fe_one();
+#pragma unroll
+    for (int s = 0; s < ZKB_DEEP_RPT; s++) {
+        const uint64_t gid = tid + (uint64_t)s * nthreads;
+        const uint32_t slot = (uint32_t)gid & ((1u << m.log_p) - 1u);
+        const uint32_t panel = (uint32_t)(gid >> m.log_p);
+        const uint32_t k = panel >> lt, t_low = panel & ((1u << lt) - 1u);
+        const uint32_t i = t_low + (slot << lt);
+        const uint32_t r = (i << m.log_beta) + k;
+        rr[s] = r;
+        const fe* row = m.data + (((size_t)panel * 2) << m.log_p) + slot;
+        fe a = fe_load(row), ab = fe_load(row + ((size_t)1 << m.log_p));
+        fe x = powtab(roots, r << (log_tab - log_N));
+        { fe x2 = fe_add(x, x); x = fe_add(x2, x); }
+        n1[s] = fe_sub(ab, abz);
+        n2[s] = fe_sub(a, azg);
+        d[2 * s] = fe_sub(x, z);
+        d[2 * s + 1] = fe_sub(x, zg);
+        pre[2 * s] = acc; acc = fe_mul(acc, d[2 * s]);
+        pre[2 * s + 1] = acc; acc = fe_mul(acc, d[2 * s + 1]);
+    }
+    fe ia = fe_inv(acc);
+#pragma unroll
+    for (int s = ZKB_DEEP_RPT - 1; s >= 0; s--) {
+        fe i2 = fe_mul(ia, pre[2 * s + 1]); ia = fe_mul(ia, d[2 * s + 1]);
+        fe i1 = fe_mul(ia, pre[2 * s]); ia = fe_mul(ia, d[2 * s]);
+        fe_store(out + rr[s], fe_add(fe_mul(n1[s], i1), fe_mul(n2[s], i2)));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9: FRI degree-respecting projection with folding factor 16 (winter-fri folding::apply_drp;
+// folding factor from src/main.rs:103).  next[i] = p_i(alpha), p_i interpolating (x_i w_16^j, e[i + j*rows]),
+// x_i = 3 * w_M^i  — the offset 3 is NOT raised to the 16th power between layers.
+struct FriFoldParams {
+    const fe* in; fe* out;
+    uint32_t log_m;            // current domain size M = 2^log_m
+    fe alpha, inv3, inv16;
+    fe w16inv[8];              // w_16^{-k}, k = 0..7
+    PowTab roots; uint32_t log_tab;
+};
+__global__ void __launch_bounds__(128) k_fri_fold16(const FriFoldParams p) {
+    const uint64_t rows = ((uint64_t)1 << p.log_m) >> 4;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    fe v[16];
+    // bit-reversed load for an in-register DIT inverse DFT
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const int br = ((j & 1) << 3) | ((j & 2) << 1) | ((j & 4) >> 1) | ((j & 8) >> 3);
+        v[br] = fe_load(p.in + i + (uint64_t)j * rows);
+    }
+#pragma unroll
+    for (int lam = 1; lam <= 4; lam++) {
+        const int half = 1 << (lam - 1);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int th = q & (half - 1);
+            const int p0 = ((q >> (lam - 1)) << lam) + th;
+            fe u = v[p0];
+            fe t = th == 0 ? v[p0 + half] : fe_mul(v[p0 + half], p.w16inv[th * (8 >> (lam - 1))]);
+            v[p0] = fe_add(u, t);
+            v[p0 + half] = fe_sub(u, t);
+        }
+    }
+    // p(alpha) = (1/16) sum_k c_k (alpha / x_i)^k,  1/x_i = (1/3) w_M^{-i}
+    const uint32_t tab_mask = (1u << p.log_tab) - 1u;
+    const uint32_t e = (0u - ((uint32_t)i << (p.log_tab - p.log_m))) & tab_mask;
+    const fe t = fe_mul(fe_mul(p.alpha, p.inv3), powtab(p.roots, e));
+    fe acc = v[15];
+#pragma unroll
+    for (int kq = 14; kq >= 0; kq--) acc = fe_add(fe_mul(acc, t), v[kq]);
+    fe_store(p.out + i, fe_mul(acc, p.inv16));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K10: ProverChannel::grind_query_seed (grinding factor from src/main.rs:101): smallest nonce >= base whose
+// Blake3(seed || nonce_le64) has >= bits trailing zeros in its first little-endian u64
+__global__ void __launch_bounds__(256) k_grind(const uint32_t* __restrict__ seed, uint64_t base, uint64_t count, uint32_t bits,
+                                               unsigned long long* __restrict__ found) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= count) return;
+    const uint64_t nonce = base + gid;
+    uint32_t m[16], cv[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) m[i] = __ldg(seed + i);
+    m[8] = (uint32_t)nonce; m[9] = (uint32_t)(nonce >> 32);
+#pragma unroll
+    for (int i = 10; i < 16; i++) m[i] = 0;
+    b3_iv(cv);
+    b3_compress(cv, m, 0, 40, B3_CHUNK_START | B3_CHUNK_END | B3_ROOT);
+    const uint64_t head = ((uint64_t)cv[1] << 32) | cv[0];
+    const uint64_t mask = bits >= 64 ? ~0ull : (((uint64_t)1 << bits) - 1ull);
+    if ((head & mask) == 0) atomicMin(found, (unsigned long long)nonce);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K11: TraceLde::query / ConstraintCommitment::query — gather LDE rows at the query positions (row-major out)
+__global__ void k_gather_lde_rows(const LdeMat m, const uint32_t* __restrict__ pos, uint32_t npos, fe* __restrict__ out) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= npos * m.w) return;
+    const uint32_t q = idx / m.w, j = idx - q * m.w;
+    const uint32_t r = __ldg(pos + q);
+    const uint32_t k = r & ((1u << m.log_beta) - 1u), i = r >> m.log_beta;
+    fe_store(out + idx, fe_load(m.data + lde_addr(m, k, i, j)));
+}
+// FriProver::build_proof / query_layer: rows [e[p + j*rows]]_{j<16}
+__global__ void k_gather_fri_rows(const fe* __restrict__ e, uint64_t rows, const uint32_t* __restrict__ pos, uint32_t npos, fe* __restrict__ out) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= npos * 16) return;
+    const uint32_t q = idx >> 4, j = idx & 15;
+    fe_store(out + idx, fe_load(e + __ldg(pos + q) + (uint64_t)j * rows));
+}
+// Merkle authentication nodes: out[i] = digests[idx[i]]
+__global__ void k_gather_digests(const uint32_t* __restrict__ digests, const uint64_t* __restrict__ idx, uint32_t count, uint32_t* __restrict__ out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count * 2) return;
+    const uint64_t src = __ldg(idx + (t >> 1));
+    reinterpret_cast<uint4*>(out)[t] = reinterpret_cast<const uint4*>(digests)[src * 2 + (t & 1)];
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-side MiMC chain trace: col_j[0] = seed_j, col_j[i+1] = (col_j[i] + rc[i mod L])^7
+// round function from src/helper.rs:213-220, constants from :404-406; output column-major [w][n]
+__global__ void k_mimc_trace(const fe* __restrict__ seeds, uint32_t w, uint64_t n, const fe* __restrict__ rc, uint32_t L, fe* __restrict__ out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= w) return;
+    fe x = fe_load(seeds + j);
+    for (uint64_t i = 0; i < n; i++) {
+        fe_store(out + (size_t)j * n + i, x);
+        fe a1 = fe_add(x, fe_ldg(rc + (i & (L - 1))));
+        fe a2 = fe_sqr(a1), a4 = fe_sqr(a2), a6 = fe_mul(a4, a2);
+        x = fe_mul(a6, a1);
+    }
+}
+
+// elementwise kernels used by tests (KATs of the device field / hash against the oracle)
+__global__ void k_test_field(const fe* a, const fe* b, fe* mul, fe* add, fe* sub, fe* inv, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe x = fe_load(a + i), y = fe_load(b + i);
+    fe_store(mul + i, fe_mul(x, y)); fe_store(add + i, fe_add(x, y)); fe_store(sub + i, fe_sub(x, y));
+    fe_store(inv + i, fe_inv(x));
+}
+__global__ void k_test_hash(const fe* data, uint32_t count, uint32_t nrows, uint32_t* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    uint32_t d[8];
+    b3_hash_elems(data + (size_t)i * count, 1, count, d);
+    for (int q = 0; q < 8; q++) out[i * 8 + q] = d[q];
+}
+
+}  // namespace zkb

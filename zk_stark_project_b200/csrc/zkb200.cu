@@ -1,0 +1,943 @@
+// libzkb200.so — B200-native STARK proving backend behind the C ABI of include/zkb200.h.
+//
+// This file is the host-side driver: it owns device memory, plans the NTT passes, issues the kernels of
+// kernels.cuh on the context's stream and runs the Fiat-Shamir channel between stages (a 32-byte root
+// up, a 16-byte challenge down).  It re-composes Winterfell 0.12's `Prover::prove` / `generate_proof`
+// (driven by the reference at /root/reference src/main.rs:228,424,468 through the Prover impls at
+// src/training/prover.rs:221-301 and src/aggregation/prover.rs:194-249) with every stage on the GPU.
+// There is no CPU fallback: without a CUDA device every entry point fails.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include "kernels.cuh"
+#include "host.hpp"
+
+namespace zkb {
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct StateError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            throw CudaError(std::string(#call) + " failed: " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                            std::to_string(__LINE__) + ")");                                                  \
+    } while (0)
+
+static thread_local std::string g_last_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) { p = nullptr; throw CudaError(std::string("cudaMalloc of ") + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e)); }
+        cap = bytes;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+static inline fe to_fe(const HF& h) {
+    fe r;
+    r.x[0] = (uint32_t)h.v; r.x[1] = (uint32_t)(h.v >> 32); r.x[2] = (uint32_t)(h.v >> 64); r.x[3] = (uint32_t)(h.v >> 96);
+    return r;
+}
+
+enum Stage { ST_IDLE = 0, ST_BEGUN, ST_TRACE, ST_EVAL, ST_COMP, ST_OOD, ST_DEEP, ST_FRI_DONE, ST_QUERY };
+
+}  // namespace zkb
+
+using namespace zkb;
+
+struct zkb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    int sm_count = 148;
+
+    // ---- per-proof state -------------------------------------------------------------------------------------
+    AirSpec air;
+    Stage stage = ST_IDLE;
+    uint32_t log_n = 0, log_beta = 0, log_N = 0, log_ce = 0, c = 0;
+    uint32_t log_tab = 0;  // root table domain (= LDE domain)
+    HostCoin coin;
+    ProofParts parts;
+    zkb_transcript ts;
+    zkb_stage_times times;
+    HF z, zg, deep_alpha;
+    std::vector<HF> ood_cur, ood_next, ood_h;
+    uint32_t fri_layer = 0, fri_layers = 0;
+    bool fri_committed = false;
+    std::vector<uint32_t> positions;
+
+    // ---- device memory (grown on demand, reused between proofs) ----------------------------------------------
+    DevBuf d_trace, d_bufA, d_bufB, d_tmp1, d_tmp2, d_lde, d_tree, d_small, d_comp_evals, d_comp_lde, d_comp_tree, d_ab, d_ab_lde,
+        d_deep, d_roots_lo, d_roots_hi, d_inv3_lo, d_inv3_hi, d_pow3, d_aux, d_gather, d_user_trace;
+    std::vector<DevBuf> d_fri_evals, d_fri_tree;
+    fe* d_polys = nullptr;  // points into bufA or bufB
+    uint32_t lde_log_p = 0, comp_log_p = 0, ab_log_p = 0;
+    uint32_t tab_log_built = 0, pow3_for_log_n = 0, pow3_for_beta = 0;
+    PowTab roots{}, inv3tab{};
+    uint32_t inv3_l1 = 0;
+    cudaEvent_t ev[16];
+    bool ev_ok = false;
+
+    // ==========================================================================================================
+    void count() { launches++; }
+    LdeMat lde_mat() const { return LdeMat{d_lde.as<fe>(), log_n, log_beta, air.w, lde_log_p}; }
+    LdeMat comp_mat() const { return LdeMat{d_comp_lde.as<fe>(), log_n, log_beta, c, comp_log_p}; }
+    LdeMat ab_mat() const { return LdeMat{d_ab_lde.as<fe>(), log_n, log_beta, 2, ab_log_p}; }
+
+    void init(int dev, void* strm) {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) throw CudaError(std::string("no CUDA device available: ") + cudaGetErrorString(e));
+        if (dev < 0 || dev >= ndev) throw InvalidArg("device index out of range");
+        device = dev;
+        CK(cudaSetDevice(device));
+        stream = (cudaStream_t)strm;
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        sm_count = prop.multiProcessorCount;
+        CK(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        for (auto& x : ev) CK(cudaEventCreate(&x));
+        ev_ok = true;
+        memset(&times, 0, sizeof(times));
+    }
+    void destroy() {
+        cudaSetDevice(device);
+        cudaStreamSynchronize(stream);
+        for (DevBuf* b : {&d_trace, &d_bufA, &d_bufB, &d_tmp1, &d_tmp2, &d_lde, &d_tree, &d_small, &d_comp_evals, &d_comp_lde, &d_comp_tree,
+                          &d_ab, &d_ab_lde, &d_deep, &d_roots_lo, &d_roots_hi, &d_inv3_lo, &d_inv3_hi, &d_pow3, &d_aux, &d_gather, &d_user_trace})
+            b->release();
+        for (auto& b : d_fri_evals) b.release();
+        for (auto& b : d_fri_tree) b.release();
+        if (ev_ok) for (auto& x : ev) cudaEventDestroy(x);
+    }
+
+    void h2d(void* dst, const void* src, size_t bytes) { CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream)); }
+    void d2h(void* dst, const void* src, size_t bytes) {
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
+    void check_launch() { CK(cudaGetLastError()); count(); }
+
+    // ---- tables ---------------------------------------------------------------------------------------------
+    static void build_powtab(HF base, uint32_t log_size, std::vector<HF>& lo, std::vector<HF>& hi, uint32_t& l1) {
+        l1 = (log_size + 1) / 2;
+        uint32_t l2 = log_size - l1;
+        lo.resize((size_t)1 << l1); hi.resize((size_t)1 << l2);
+        HF x = HF::raw(1);
+        for (auto& v : lo) { v = x; x = x * base; }
+        HF step = x;  // base^(2^l1)
+        x = HF::raw(1);
+        for (auto& v : hi) { v = x; x = x * step; }
+    }
+    void ensure_tables() {
+        if (tab_log_built != log_N) {
+            std::vector<HF> lo, hi; uint32_t l1;
+            build_powtab(HF::root_of_unity(log_N), log_N, lo, hi, l1);
+            d_roots_lo.ensure(lo.size() * 16); d_roots_hi.ensure(hi.size() * 16);
+            h2d(d_roots_lo.p, lo.data(), lo.size() * 16); h2d(d_roots_hi.p, hi.data(), hi.size() * 16);
+            roots = PowTab{d_roots_lo.as<fe>(), d_roots_hi.as<fe>(), l1};
+            build_powtab(HF::from_u64(3).inv(), log_N, lo, hi, l1);
+            d_inv3_lo.ensure(lo.size() * 16); d_inv3_hi.ensure(hi.size() * 16);
+            h2d(d_inv3_lo.p, lo.data(), lo.size() * 16); h2d(d_inv3_hi.p, hi.data(), hi.size() * 16);
+            inv3tab = PowTab{d_inv3_lo.as<fe>(), d_inv3_hi.as<fe>(), l1};
+            CK(cudaStreamSynchronize(stream));  // host vectors go out of scope
+            tab_log_built = log_N;
+            pow3_for_log_n = 0;
+        }
+        log_tab = log_N;
+        if (pow3_for_log_n != log_n) {
+            std::vector<HF> p3(log_n + 1);
+            for (uint32_t l = 0; l <= log_n; l++) p3[l] = HF::from_u64(3).pow((u128)(air.n >> l));
+            d_pow3.ensure(64 * 16);
+            h2d(d_pow3.p, p3.data(), p3.size() * 16);
+            CK(cudaStreamSynchronize(stream));
+            pow3_for_log_n = log_n;
+        }
+    }
+
+    // ---- NTT planning ---------------------------------------------------------------------------------------
+    static uint32_t pick_cj(uint32_t ncols) { return ncols >= 9 ? 16 : ncols >= 5 ? 8 : ncols >= 3 ? 4 : ncols == 2 ? 2 : 1; }
+    static std::vector<uint32_t> plan_layers(uint32_t log_len, uint32_t cj) {
+        uint32_t maxlog = 12 - log2u(cj);  // S * cj <= 4096 elements in shared memory
+        uint32_t passes = (log_len + maxlog - 1) / maxlog;
+        if (passes == 0) passes = 1;
+        std::vector<uint32_t> b;  // cumulative layer boundaries
+        uint32_t done = 0;
+        for (uint32_t q = 0; q < passes; q++) { uint32_t take = (log_len - done + (passes - q) - 1) / (passes - q); done += take; b.push_back(done); }
+        return b;
+    }
+    void launch_pass(NttPass& p) {
+        const uint32_t S = 1u << (p.b - p.a);
+        const uint32_t rs = p.cj + (p.cj > 1 ? 1 : 0);
+        const size_t smem = ((size_t)S * rs + S) * 16;
+        const uint64_t tiles = (uint64_t)((p.ncols + p.cj - 1) / p.cj) * p.n_cosets * ((uint64_t)1 << (p.log_n - (p.b - p.a)));
+        if (tiles > 0x7fffffffull) throw InvalidArg("transform too large for one launch");
+        k_ntt_pass<<<(unsigned)tiles, 256, smem, stream>>>(p);
+        check_launch();
+    }
+    // generic multi-pass transform of `ncols` columns of length 2^log_len.
+    //  in : row-major [len][w_in] (column window col0_in..)         bufs: scratch buffers for intermediate passes
+    //  out: row-major natural [len][w_out] (inverse / plain) or the panel layout (coset LDE, one launch per coset batch)
+    struct Xform {
+        const fe* in; uint32_t w_in, col0_in;
+        fe* out; uint32_t w_out, col0_out;
+        uint32_t ncols, log_len;
+        bool inverse, coset_lde;
+        uint32_t log_lde;  // coset LDE only
+        bool scale; HF scale_by;
+    };
+    // returns log_p of the panel layout for LDEs (size of the last pass)
+    uint32_t run_xform(const Xform& x, DevBuf& s1, DevBuf& s2) {
+        const uint32_t cj = pick_cj(x.ncols);
+        std::vector<uint32_t> bnd = plan_layers(x.log_len, cj);
+        const uint32_t passes = (uint32_t)bnd.size();
+        const uint64_t len = (uint64_t)1 << x.log_len;
+        const uint32_t n_cosets = x.coset_lde ? (1u << (x.log_lde - x.log_len)) : 1;
+        // coset batches bound the scratch size
+        uint32_t batch = n_cosets;
+        if (passes > 1) {
+            const uint64_t per = len * x.ncols * 16;
+            uint64_t budget = (uint64_t)6 << 30;
+            batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_cosets, budget / std::max<uint64_t>(per, 1)));
+            s1.ensure(per * batch);
+            if (passes > 2) s2.ensure(per * batch);
+        }
+        for (uint32_t k0 = 0; k0 < n_cosets; k0 += batch) {
+            const uint32_t nk = std::min(batch, n_cosets - k0);
+            uint32_t a = 0;
+            const fe* src = x.in; uint32_t w_src = x.w_in, c0_src = x.col0_in; uint64_t src_stride = 0;
+            for (uint32_t q = 0; q < passes; q++) {
+                NttPass p{};
+                const bool last = (q + 1 == passes);
+                p.in = src; p.w_in = w_src; p.col0_in = c0_src; p.in_coset_stride = src_stride;
+                p.log_n = x.log_len; p.a = a; p.b = bnd[q];
+                p.ncols = x.ncols; p.cj = cj; p.n_cosets = nk; p.coset0 = k0;
+                p.coset = x.coset_lde ? 1 : 0; p.inverse = x.inverse ? 1 : 0;
+                p.log_tab = log_tab; p.log_lde = x.coset_lde ? x.log_lde : 0;
+                p.roots = roots; p.pow3 = d_pow3.as<fe>();
+                if (last) {
+                    p.out = x.out; p.w_out = x.w_out; p.col0_out = x.col0_out;
+                    p.out_panel = x.coset_lde ? 1 : 0;
+                    p.out_coset_stride = 0;
+                    p.do_scale = x.scale ? 1 : 0; p.scale = to_fe(x.scale_by);
+                } else {
+                    fe* dst = (q % 2 == 0) ? s1.as<fe>() : s2.as<fe>();
+                    p.out = dst; p.w_out = x.ncols; p.col0_out = 0; p.out_coset_stride = len * x.ncols;
+                    src = dst; w_src = x.ncols; c0_src = 0; src_stride = len * x.ncols;
+                }
+                launch_pass(p);
+                a = bnd[q];
+            }
+        }
+        return bnd.back() - (passes > 1 ? bnd[passes - 2] : 0);
+    }
+
+    // ---- Merkle heap: heap[1] root, heap[N + l] leaves -----------------------------------------------------------
+    void build_merkle(uint32_t* heap, uint64_t n_leaves) {
+        for (uint64_t lvl = n_leaves / 2; lvl >= 1; lvl >>= 1) {
+            k_merkle_level<<<(unsigned)((lvl + 255) / 256), 256, 0, stream>>>(heap + 2 * lvl * 8, heap + lvl * 8, lvl);
+            check_launch();
+        }
+    }
+
+    // ==========================================================================================================
+    // stages
+    void begin(const zkb_air_desc* desc) {
+        CK(cudaSetDevice(device));
+        air = AirSpec::from_desc(desc);
+        log_n = log2u(air.n); log_beta = log2u(air.blowup); log_N = log_n + log_beta;
+        log_ce = log2u(air.ce_blowup()); c = air.num_comp_cols();
+        if ((1u << log_ce) > air.blowup) throw InvalidArg("constraint evaluation blowup exceeds the LDE blowup");
+        {   // distinct assertion steps = boundary groups
+            std::set<uint64_t> steps;
+            for (auto& a : air.assertions) steps.insert(a.step);
+            if (steps.size() > ZKB_MAX_GROUPS) throw InvalidArg("too many distinct assertion steps (boundary groups)");
+        }
+        ensure_tables();
+        parts = ProofParts();
+        memset(&ts, 0, sizeof(ts));
+        ts.comp_degree_ok = 1;
+        memset(&times, 0, sizeof(times));
+        coin.init(air.coin_seed());
+        fri_layers = air.num_fri_layers();
+        if (fri_layers > 16) throw InvalidArg("too many FRI layers");
+        fri_layer = 0; fri_committed = false;
+        positions.clear();
+        stage = ST_BEGUN;
+    }
+
+    // K1-K4.  src: column-major [w][n] in device memory
+    void trace_commit_device(const fe* d_src, uint8_t root_out[32]) {
+        if (stage != ST_BEGUN) throw StateError("zkb_trace_commit: call zkb_begin first");
+        const uint64_t n = air.n, N = air.lde_size();
+        const uint32_t w = air.w;
+        CK(cudaEventRecord(ev[1], stream));
+        // K1: transpose + inverse NTT -> polys row-major [n][w]
+        d_bufA.ensure(n * w * 16); d_bufB.ensure(n * w * 16);
+        {
+            dim3 grid((unsigned)((n + 31) / 32), (w + 31) / 32), block(32, 8);
+            k_transpose_cols<<<grid, block, 0, stream>>>(d_src, d_bufA.as<fe>(), (uint32_t)n, w);
+            check_launch();
+        }
+        {
+            Xform x{d_bufA.as<fe>(), w, 0, d_bufB.as<fe>(), w, 0, w, log_n, true, false, 0, true, HF::from_u64(n).inv()};
+            run_xform(x, d_tmp1, d_tmp2);
+            d_polys = d_bufB.as<fe>();
+        }
+        CK(cudaEventRecord(ev[2], stream));
+        // K2: coset LDE into the panel layout
+        d_lde.ensure(N * w * 16);
+        {
+            Xform x{d_polys, w, 0, d_lde.as<fe>(), w, 0, w, log_n, false, true, log_N, false, HF()};
+            lde_log_p = run_xform(x, d_tmp1, d_tmp2);
+        }
+        CK(cudaEventRecord(ev[3], stream));
+        // K3: leaves
+        d_tree.ensure(2 * N * 32);
+        k_hash_lde_rows<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(lde_mat(), d_tree.as<uint32_t>() + N * 8);
+        check_launch();
+        CK(cudaEventRecord(ev[4], stream));
+        // K4: tree
+        build_merkle(d_tree.as<uint32_t>(), N);
+        CK(cudaEventRecord(ev[5], stream));
+        Digest32 root;
+        d2h(root.b, d_tree.as<uint32_t>() + 8, 32);
+        parts.commitments.push_back(root);
+        memcpy(ts.trace_root, root.b, 32);
+        if (root_out) memcpy(root_out, root.b, 32);
+        CK(cudaEventElapsedTime(&times.interpolate, ev[1], ev[2]));
+        CK(cudaEventElapsedTime(&times.lde, ev[2], ev[3]));
+        CK(cudaEventElapsedTime(&times.leaf_hash, ev[3], ev[4]));
+        CK(cudaEventElapsedTime(&times.merkle, ev[4], ev[5]));
+        stage = ST_TRACE;
+    }
+    const fe* upload_cols(const uint8_t* const* cols, uint32_t w, uint64_t n, DevBuf& dst) {
+        if (!cols) throw InvalidArg("null trace columns");
+        dst.ensure((size_t)w * n * 16);
+        bool contiguous = true;
+        for (uint32_t j = 0; j < w; j++) { if (!cols[j]) throw InvalidArg("null trace column"); if (cols[j] != cols[0] + (size_t)j * n * 16) contiguous = false; }
+        if (contiguous) h2d(dst.p, cols[0], (size_t)w * n * 16);
+        else for (uint32_t j = 0; j < w; j++) h2d((uint8_t*)dst.p + (size_t)j * n * 16, cols[j], n * 16);
+        return dst.as<fe>();
+    }
+    void trace_commit_host(const uint8_t* const* cols, uint8_t root_out[32]) {
+        if (stage != ST_BEGUN) throw StateError("zkb_trace_commit: call zkb_begin first");
+        CK(cudaEventRecord(ev[0], stream));
+        const fe* d = upload_cols(cols, air.w, air.n, d_trace);
+        trace_commit_device(d, root_out);
+        CK(cudaEventElapsedTime(&times.h2d, ev[0], ev[1]));
+    }
+
+    // K5
+    void constraints_eval(const HF& alpha, uint8_t* evals_out) {
+        if (stage != ST_TRACE) throw StateError("zkb_constraints_eval: trace is not committed");
+        CK(cudaEventRecord(ev[0], stream));
+        const uint32_t nt = air.num_transition(), na = (uint32_t)air.assertions.size();
+        const uint64_t n = air.n, ce = (uint64_t)1 << log_ce;
+        // ConstraintCompositionCoefficients::draw_algebraic: alpha^0.. for transition, continuing for boundary  [A.5]
+        std::vector<HF> tcoef(nt), acoef(na), aval(na);
+        std::vector<uint32_t> acol(na);
+        { HF cur = HF::raw(1); for (auto& x : tcoef) { x = cur; cur = cur * alpha; } for (auto& x : acoef) { x = cur; cur = cur * alpha; } }
+        EvalParams p{};
+        p.lde = lde_mat(); p.air_id = air.id; p.log_ce = log_ce; p.n_trans = nt;
+        const HF g = HF::root_of_unity(log_n);
+        uint32_t ng = 0;
+        for (uint32_t i = 0; i < na; i++) {
+            if (i == 0 || air.assertions[i].step != air.assertions[i - 1].step) {
+                p.g_off[ng] = i; p.g_point[ng] = to_fe(g.pow(air.assertions[i].step)); ng++;
+            }
+            acol[i] = air.assertions[i].col; aval[i] = air.assertions[i].value;
+        }
+        p.g_off[ng] = na; p.n_groups = ng;
+        // 1/(x^n - 1) on the cosets used by the ce domain: x^n = 3^n * w_beta^k, k = kc * beta/ce
+        std::vector<HF> zinv(ce);
+        { HF on = HF::from_u64(3).pow((u128)n), wb = HF::root_of_unity(log_beta);
+          for (uint64_t kc = 0; kc < ce; kc++) zinv[kc] = (on * wb.pow((u128)(kc << (log_beta - log_ce))) - HF::raw(1)).inv(); }
+        // periodic column over the ce domain (PeriodicValueTable): P_L((x)^(n/L)) tabulated on 3^(n/L) * <w_{L*ce}>
+        std::vector<HF> per;
+        if (air.id == ZKB_AIR_ID_MIMC) {
+            const size_t L = air.params.size();
+            std::vector<HF> poly = host_interpolate(air.params, HF::raw(1));
+            const HF off = HF::from_u64(3).pow((u128)(n / L)), wl = HF::root_of_unity(log2u(L * ce));
+            per.resize(L * ce);
+            HF x = off;
+            for (size_t t = 0; t < L * ce; t++) { HF acc; for (size_t q = L; q-- > 0;) acc = acc * x + poly[q]; per[t] = acc; x = x * wl; }
+        }
+        // pack the small arrays into one device buffer
+        size_t off_t = 0, off_c = off_t + nt * 16, off_v = off_c + na * 16, off_z = off_v + na * 16, off_p = off_z + ce * 16,
+               off_col = off_p + per.size() * 16, total = off_col + na * 4;
+        std::vector<uint8_t> pack(total);
+        memcpy(&pack[off_t], tcoef.data(), nt * 16); memcpy(&pack[off_c], acoef.data(), na * 16); memcpy(&pack[off_v], aval.data(), na * 16);
+        memcpy(&pack[off_z], zinv.data(), ce * 16); if (!per.empty()) memcpy(&pack[off_p], per.data(), per.size() * 16);
+        memcpy(&pack[off_col], acol.data(), na * 4);
+        d_aux.ensure(total);
+        h2d(d_aux.p, pack.data(), total);
+        uint8_t* base = d_aux.as<uint8_t>();
+        p.tcoef = (const fe*)(base + off_t); p.a_coef = (const fe*)(base + off_c); p.a_val = (const fe*)(base + off_v);
+        p.zinv = (const fe*)(base + off_z); p.periodic = (const fe*)(base + off_p); p.a_col = (const uint32_t*)(base + off_col);
+        p.per_mask = per.empty() ? 0 : (uint32_t)per.size() - 1;
+        p.g_last = to_fe(g.pow((u128)(n - 1)));
+        p.k = air.id == ZKB_AIR_ID_AGGREGATION ? to_fe(air.params[0]) : fe{};
+        p.roots = roots; p.log_tab = log_tab;
+        d_comp_evals.ensure(n * ce * 16);
+        p.out = d_comp_evals.as<fe>();
+        const uint64_t threads = n * ce;
+        k_eval_constraints<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(p);
+        check_launch();
+        CK(cudaStreamSynchronize(stream));  // `pack` must outlive the copy
+        CK(cudaEventRecord(ev[1], stream));
+        if (evals_out) d2h(evals_out, d_comp_evals.p, n * ce * 16);
+        CK(cudaEventSynchronize(ev[1]));
+        CK(cudaEventElapsedTime(&times.constraints, ev[0], ev[1]));
+        stage = ST_EVAL;
+    }
+
+    // K6
+    void constraints_commit(uint8_t root_out[32]) {
+        if (stage != ST_EVAL) throw StateError("zkb_constraints_commit: constraints are not evaluated");
+        CK(cudaEventRecord(ev[0], stream));
+        const uint64_t n = air.n, N = air.lde_size(), cen = n << log_ce;
+        // CompositionPoly::new: interpolate over 3*<w_{ce n}>, then split into c columns of n coefficients
+        d_bufA.ensure(cen * 16);
+        fe* coef = d_bufA.as<fe>();  // the trace-sized transposed input is dead by now
+        {
+            Xform x{d_comp_evals.as<fe>(), 1, 0, coef, 1, 0, 1, log_n + log_ce, true, false, 0, false, HF()};
+            run_xform(x, d_tmp1, d_tmp2);
+            // inv3tab covers exponents < 2^log_N >= ce*n
+            k_scale_pow<<<(unsigned)((cen + 255) / 256), 256, 0, stream>>>(coef, cen, inv3tab, to_fe(HF::from_u64(cen).inv()));
+            check_launch();
+        }
+        // evaluate the c column polynomials over the LDE domain (panel layout, width c)
+        d_comp_lde.ensure(N * c * 16);
+        for (uint32_t i = 0; i < c; i++) {
+            Xform x{coef + (size_t)i * n, 1, 0, d_comp_lde.as<fe>(), c, i, 1, log_n, false, true, log_N, false, HF()};
+            comp_log_p = run_xform(x, d_tmp1, d_tmp2);
+        }
+        d_comp_tree.ensure(2 * N * 32);
+        k_hash_lde_rows<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(comp_mat(), d_comp_tree.as<uint32_t>() + N * 8);
+        check_launch();
+        build_merkle(d_comp_tree.as<uint32_t>(), N);
+        CK(cudaEventRecord(ev[1], stream));
+        Digest32 root;
+        d2h(root.b, d_comp_tree.as<uint32_t>() + 8, 32);
+        parts.commitments.push_back(root);
+        memcpy(ts.constraint_root, root.b, 32);
+        if (root_out) memcpy(root_out, root.b, 32);
+        CK(cudaEventElapsedTime(&times.composition, ev[0], ev[1]));
+        stage = ST_COMP;
+    }
+
+    // K7
+    void ood_eval(const HF& z_) {
+        if (stage != ST_COMP) throw StateError("zkb_ood_eval: constraint commitment is missing");
+        CK(cudaEventRecord(ev[0], stream));
+        z = z_; zg = z * HF::root_of_unity(log_n);
+        const uint64_t n = air.n; const uint32_t w = air.w;
+        const uint32_t R = 128;
+        const uint32_t nch = (uint32_t)((n + R - 1) / R);
+        std::vector<HF> zp(2 * nch);
+        { HF zr = z.pow(R), zgr = zg.pow(R), a = HF::raw(1), b = HF::raw(1);
+          for (uint32_t q = 0; q < nch; q++) { zp[q] = a; zp[nch + q] = b; a = a * zr; b = b * zgr; } }
+        // layout of d_small: [zpow nch][zgpow nch][part_z nch*w][part_zg nch*w][ood 2w][hpart ...]
+        const uint32_t Q = 64;
+        const uint32_t nt = (uint32_t)((n + Q - 1) / Q);
+        size_t o_zp = 0, o_pz = o_zp + 2 * (size_t)nch, o_pzg = o_pz + (size_t)nch * w, o_ood = o_pzg + (size_t)nch * w,
+               o_hp = o_ood + 2 * (size_t)w, total = o_hp + (size_t)c * nt;
+        d_small.ensure(total * 16);
+        fe* sm = d_small.as<fe>();
+        h2d(sm + o_zp, zp.data(), zp.size() * 16);
+        k_ood_partial<<<nch, 256, 0, stream>>>(d_polys, (uint32_t)n, w, R, to_fe(z), to_fe(zg), sm + o_zp, sm + o_zp + nch, sm + o_pz, sm + o_pzg);
+        check_launch();
+        k_col_sum<<<(w + 127) / 128, 128, 0, stream>>>(sm + o_pz, nch, w, sm + o_ood);
+        check_launch();
+        k_col_sum<<<(w + 127) / 128, 128, 0, stream>>>(sm + o_pzg, nch, w, sm + o_ood + w);
+        check_launch();
+        // H_i(z) from the composition column coefficients (still in d_bufA)
+        {
+            dim3 grid((nt + 255) / 256, c);
+            k_poly_eval_partial<<<grid, 256, 0, stream>>>(d_bufA.as<fe>(), (uint32_t)n, Q, to_fe(z), to_fe(z.pow(Q)), sm + o_hp);
+            check_launch();
+        }
+        std::vector<HF> host(2 * (size_t)w + (size_t)c * nt);
+        d2h(host.data(), sm + o_ood, host.size() * 16);  // ood and hpart are adjacent
+        ood_cur.assign(host.begin(), host.begin() + w);
+        ood_next.assign(host.begin() + w, host.begin() + 2 * w);
+        ood_h.assign(c, HF());
+        for (uint32_t i = 0; i < c; i++) { HF s; for (uint32_t t = 0; t < nt; t++) s = s + host[2 * (size_t)w + (size_t)i * nt + t]; ood_h[i] = s; }
+        CK(cudaEventRecord(ev[1], stream));
+        CK(cudaEventSynchronize(ev[1]));
+        CK(cudaEventElapsedTime(&times.ood, ev[0], ev[1]));
+        stage = ST_OOD;
+    }
+
+    // K8
+    void deep_compose(const HF& alpha) {
+        if (stage != ST_OOD) throw StateError("zkb_deep_compose: OOD frame is missing");
+        CK(cudaEventRecord(ev[0], stream));
+        deep_alpha = alpha;
+        const uint64_t n = air.n, N = air.lde_size(); const uint32_t w = air.w;
+        // DeepCompositionCoefficients::draw_algebraic: alpha^0.. for trace columns, continuing for H columns  [A.5]
+        std::vector<HF> g(w + c);
+        { HF cur = HF::raw(1); for (auto& x : g) { x = cur; cur = cur * alpha; } }
+        HF az, azg, bz;
+        for (uint32_t j = 0; j < w; j++) { az = az + g[j] * ood_cur[j]; azg = azg + g[j] * ood_next[j]; }
+        for (uint32_t i = 0; i < c; i++) bz = bz + g[w + i] * ood_h[i];
+        d_aux.ensure((w + c) * 16);
+        h2d(d_aux.p, g.data(), g.size() * 16);
+        d_ab.ensure(n * 2 * 16);
+        k_deep_combine<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(d_polys, (uint32_t)n, w, d_aux.as<fe>(), d_bufA.as<fe>(), c,
+                                                                          d_aux.as<fe>() + w, d_ab.as<fe>());
+        check_launch();
+        CK(cudaStreamSynchronize(stream));  // `g` must outlive the copy
+        d_ab_lde.ensure(N * 2 * 16);
+        {
+            Xform x{d_ab.as<fe>(), 2, 0, d_ab_lde.as<fe>(), 2, 0, 2, log_n, false, true, log_N, false, HF()};
+            ab_log_p = run_xform(x, d_tmp1, d_tmp2);
+        }
+        d_deep.ensure(N * 16);
+        const uint64_t threads = N / ZKB_DEEP_RPT;
+        k_deep_eval<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(ab_mat(), to_fe(z), to_fe(zg), to_fe(az), to_fe(az + bz), to_fe(azg),
+                                                                          roots, log_tab, d_deep.as<fe>());
+        check_launch();
+        CK(cudaEventRecord(ev[1], stream));
+        CK(cudaEventSynchronize(ev[1]));
+        CK(cudaEventElapsedTime(&times.deep, ev[0], ev[1]));
+        if (d_fri_evals.size() < fri_layers + 1) { d_fri_evals.resize(fri_layers + 1); d_fri_tree.resize(fri_layers + 1); }
+        fri_layer = 0; fri_committed = false;
+        stage = ST_DEEP;
+    }
+
+    // K9
+    const fe* fri_cur_evals() const { return fri_layer == 0 ? d_deep.as<fe>() : d_fri_evals[fri_layer].as<fe>(); }
+    uint64_t fri_domain(uint32_t layer) const { return air.lde_size() >> (4 * layer); }
+    void fri_commit_layer(uint8_t root_out[32]) {
+        if (stage != ST_DEEP || fri_layer >= fri_layers || fri_committed) throw StateError("zkb_fri_commit_layer: out of order");
+        const uint64_t M = fri_domain(fri_layer), rows = M / 16;
+        DevBuf& tree = d_fri_tree[fri_layer];
+        tree.ensure(2 * rows * 32);
+        k_hash_strided_rows<<<(unsigned)((rows + 127) / 128), 128, 0, stream>>>(fri_cur_evals(), rows, 16, tree.as<uint32_t>() + rows * 8);
+        check_launch();
+        build_merkle(tree.as<uint32_t>(), rows);
+        Digest32 root;
+        d2h(root.b, tree.as<uint32_t>() + 8, 32);
+        parts.commitments.push_back(root);
+        memcpy(ts.fri_roots[fri_layer], root.b, 32);
+        if (root_out) memcpy(root_out, root.b, 32);
+        fri_committed = true;
+    }
+    void fri_fold(const HF& alpha) {
+        if (stage != ST_DEEP || !fri_committed) throw StateError("zkb_fri_fold: commit the layer first");
+        const uint64_t M = fri_domain(fri_layer), rows = M / 16;
+        alpha.to_bytes(ts.fri_alphas[fri_layer]);
+        DevBuf& nxt = d_fri_evals[fri_layer + 1];
+        nxt.ensure(rows * 16);
+        FriFoldParams p{};
+        p.in = fri_cur_evals(); p.out = nxt.as<fe>(); p.log_m = log2u(M);
+        p.alpha = to_fe(alpha); p.inv3 = to_fe(HF::from_u64(3).inv()); p.inv16 = to_fe(HF::from_u64(16).inv());
+        HF wi = HF::root_of_unity(4).inv(), x = HF::raw(1);
+        for (int q = 0; q < 8; q++) { p.w16inv[q] = to_fe(x); x = x * wi; }
+        p.roots = roots; p.log_tab = log_tab;
+        k_fri_fold16<<<(unsigned)((rows + 127) / 128), 128, 0, stream>>>(p);
+        check_launch();
+        fri_layer++;
+        fri_committed = false;
+        ts.n_fri_layers = fri_layer;
+    }
+    void fri_remainder(Digest32* commitment) {
+        if (stage != ST_DEEP || fri_layer != fri_layers || fri_committed) throw StateError("zkb_fri_remainder: fold all layers first");
+        const uint64_t M = fri_domain(fri_layer);
+        std::vector<HF> ev_(M);
+        d2h(ev_.data(), fri_cur_evals(), M * 16);
+        std::vector<HF> coef = host_interpolate(ev_, HF::from_u64(3));  // set_remainder  [A.10]
+        const uint64_t rs = M / air.blowup;
+        parts.remainder.assign(coef.begin(), coef.begin() + rs);
+        std::reverse(parts.remainder.begin(), parts.remainder.end());
+        Digest32 d;
+        HostCoin::hash_elems(parts.remainder, d.b);
+        parts.commitments.push_back(d);
+        memcpy(ts.remainder_commitment, d.b, 32);
+        if (commitment) *commitment = d;
+        stage = ST_FRI_DONE;
+    }
+
+    // K10
+    uint64_t grind(const uint8_t seed[32], uint32_t bits) {
+        if (bits > 32) throw InvalidArg("grinding factor must be <= 32");
+        d_gather.ensure(4096);
+        uint32_t* d_seed = d_gather.as<uint32_t>();
+        unsigned long long* d_found = reinterpret_cast<unsigned long long*>(d_gather.as<uint8_t>() + 64);
+        h2d(d_seed, seed, 32);
+        unsigned long long init = ~0ull;
+        h2d(d_found, &init, 8);
+        uint64_t base = 1;
+        const uint64_t window = (uint64_t)1 << 22;
+        for (;;) {
+            k_grind<<<(unsigned)(window / 256), 256, 0, stream>>>(d_seed, base, window, bits, d_found);
+            check_launch();
+            unsigned long long f;
+            d2h(&f, d_found, 8);
+            if (f != ~0ull) return f;
+            base += window;
+            if (base > ((uint64_t)1 << 44)) throw std::runtime_error("proof-of-work nonce not found");
+        }
+    }
+
+    // K11
+    void query(uint32_t which, const std::vector<uint32_t>& pos, std::vector<uint8_t>& rows, std::vector<uint8_t>& paths) {
+        const uint32_t np = (uint32_t)pos.size();
+        if (np == 0 || np > 255) throw InvalidArg("bad number of query positions");
+        uint32_t width, depth; const uint32_t* heap;
+        uint64_t domain;
+        if (which == 0) { width = air.w; domain = air.lde_size(); heap = d_tree.as<uint32_t>(); }
+        else if (which == 1) { width = c; domain = air.lde_size(); heap = d_comp_tree.as<uint32_t>(); }
+        else {
+            uint32_t l = which - 2;
+            if (l >= fri_layers) throw InvalidArg("no such FRI layer");
+            width = 16; domain = fri_domain(l) / 16; heap = d_fri_tree[l].as<uint32_t>();
+        }
+        for (uint32_t p : pos) if (p >= domain) throw InvalidArg("query position out of range");
+        depth = log2u(domain);
+        std::vector<std::vector<uint64_t>> plan = plan_batch_proof(depth, pos);
+        std::vector<uint64_t> flat;
+        for (auto& v : plan) flat.insert(flat.end(), v.begin(), v.end());
+        // device scratch: [positions np u32][idx flat u64][rows np*width fe][digests flat*32]
+        size_t o_pos = 0, o_idx = 1024, o_rows = o_idx + ((flat.size() * 8 + 15) / 16) * 16 + 16, o_dig = o_rows + (size_t)np * width * 16,
+               total = o_dig + flat.size() * 32 + 32;
+        d_gather.ensure(total);
+        uint8_t* base = d_gather.as<uint8_t>();
+        h2d(base + o_pos, pos.data(), np * 4);
+        if (!flat.empty()) h2d(base + o_idx, flat.data(), flat.size() * 8);
+        const uint32_t th = np * width;
+        if (which == 0) k_gather_lde_rows<<<(th + 127) / 128, 128, 0, stream>>>(lde_mat(), (const uint32_t*)(base + o_pos), np, (fe*)(base + o_rows));
+        else if (which == 1) k_gather_lde_rows<<<(th + 127) / 128, 128, 0, stream>>>(comp_mat(), (const uint32_t*)(base + o_pos), np, (fe*)(base + o_rows));
+        else {
+            uint32_t l = which - 2;
+            const fe* e = l == 0 ? d_deep.as<fe>() : d_fri_evals[l].as<fe>();
+            k_gather_fri_rows<<<(th + 127) / 128, 128, 0, stream>>>(e, domain, (const uint32_t*)(base + o_pos), np, (fe*)(base + o_rows));
+        }
+        check_launch();
+        if (!flat.empty()) {
+            k_gather_digests<<<(unsigned)((flat.size() * 2 + 127) / 128), 128, 0, stream>>>(heap, (const uint64_t*)(base + o_idx), (uint32_t)flat.size(),
+                                                                                        (uint32_t*)(base + o_dig));
+            check_launch();
+        }
+        std::vector<uint8_t> host((size_t)np * width * 16 + flat.size() * 32);
+        d2h(host.data(), base + o_rows, host.size());  // rows and digests are adjacent
+        rows.assign(host.begin(), host.begin() + (size_t)np * width * 16);
+        paths = batch_proof_bytes(depth, plan, host.data() + (size_t)np * width * 16);
+    }
+
+    // ==========================================================================================================
+    // Prover::prove: the whole pipeline with the channel on the host  
+    std::vector<uint8_t> prove(const zkb_air_desc* desc, const uint8_t* const* cols, const fe* d_trace_in, uint64_t force_nonce) {
+        begin(desc);
+        CK(cudaEventRecord(ev[14], stream));
+        uint8_t root[32];
+        if (d_trace_in) trace_commit_device(d_trace_in, root); else trace_commit_host(cols, root);
+        coin.reseed(root);                                   // channel.commit_trace
+        HF alpha = coin.draw();                              // get_constraint_composition_coeffs
+        alpha.to_bytes(ts.constraint_alpha);
+        constraints_eval(alpha, nullptr);
+        constraints_commit(root);
+        coin.reseed(root);                                   // channel.commit_constraints
+        HF zz = coin.draw();                                 // get_ood_point
+        zz.to_bytes(ts.z);
+        ood_eval(zz);
+        parts.ood_trace_interleaved.resize(2 * (size_t)air.w);  // [T_0(z), T_0(zg), T_1(z), ...]  [A.5]
+        for (uint32_t j = 0; j < air.w; j++) { parts.ood_trace_interleaved[2 * j] = ood_cur[j]; parts.ood_trace_interleaved[2 * j + 1] = ood_next[j]; }
+        parts.ood_h = ood_h;
+        uint8_t h[32];
+        HostCoin::hash_elems(parts.ood_trace_interleaved, h); coin.reseed(h);  // send_ood_trace_states
+        HostCoin::hash_elems(parts.ood_h, h); coin.reseed(h);                  // send_ood_constraint_evaluations
+        HF da = coin.draw();                                 // get_deep_composition_coeffs
+        da.to_bytes(ts.deep_alpha);
+        deep_compose(da);
+        CK(cudaEventRecord(ev[2], stream));
+        for (uint32_t l = 0; l < fri_layers; l++) {          // FriProver::build_layers
+            fri_commit_layer(root);
+            coin.reseed(root);
+            fri_fold(coin.draw());
+        }
+        Digest32 rc;
+        fri_remainder(&rc);
+        coin.reseed(rc.b);
+        CK(cudaEventRecord(ev[3], stream));
+        uint64_t nonce = force_nonce ? force_nonce : grind(coin.seed, air.grinding);  // grind_query_seed
+        CK(cudaEventRecord(ev[4], stream));
+        parts.nonce = nonce; ts.pow_nonce = nonce;
+        positions = coin.draw_integers(air.num_queries, air.lde_size(), nonce);        // get_query_positions
+        std::sort(positions.begin(), positions.end());
+        positions.erase(std::unique(positions.begin(), positions.end()), positions.end());
+        parts.n_unique = (uint32_t)positions.size();
+        ts.n_positions = parts.n_unique;
+        for (size_t i = 0; i < positions.size() && i < 256; i++) ts.positions[i] = positions[i];
+        {   // FriProver::build_proof, TraceLde::query, ConstraintCommitment::query
+            std::vector<uint32_t> pos = positions;
+            uint64_t dom = air.lde_size();
+            parts.fri_rows.resize(fri_layers); parts.fri_paths.resize(fri_layers);
+            for (uint32_t l = 0; l < fri_layers; l++) {
+                pos = fold_positions(pos, dom, 16);
+                query(2 + l, pos, parts.fri_rows[l], parts.fri_paths[l]);
+                dom /= 16;
+            }
+            query(0, positions, parts.trace_rows, parts.trace_paths);
+            query(1, positions, parts.comp_rows, parts.comp_paths);
+        }
+        CK(cudaEventRecord(ev[15], stream));
+        CK(cudaEventSynchronize(ev[15]));
+        CK(cudaEventElapsedTime(&times.fri, ev[2], ev[3]));
+        CK(cudaEventElapsedTime(&times.grind, ev[3], ev[4]));
+        CK(cudaEventElapsedTime(&times.queries, ev[4], ev[15]));
+        CK(cudaEventElapsedTime(&times.total, ev[14], ev[15]));
+        stage = ST_QUERY;
+        return serialize_proof(air, parts);
+    }
+};
+
+// ================================================================================================================
+// C ABI
+template <class F>
+static int32_t guarded(zkb_ctx* ctx, F&& f) {
+    try {
+        if (!ctx) throw InvalidArg("null context");
+        f();
+        return ZKB_OK;
+    } catch (const InvalidArg& e) { (ctx ? ctx->err : g_last_error) = e.what(); return ZKB_ERR_INVALID; }
+    catch (const StateError& e) { (ctx ? ctx->err : g_last_error) = e.what(); return ZKB_ERR_STATE; }
+    catch (const CudaError& e) {
+        (ctx ? ctx->err : g_last_error) = e.what();
+        return std::string(e.what()).find("out of memory") != std::string::npos ? ZKB_ERR_OOM : ZKB_ERR_CUDA;
+    } catch (const std::exception& e) { (ctx ? ctx->err : g_last_error) = e.what(); return ZKB_ERR_INVALID; }
+}
+static uint8_t* dup_bytes(const std::vector<uint8_t>& v) {
+    uint8_t* p = (uint8_t*)malloc(v.size() ? v.size() : 1);
+    if (v.size()) memcpy(p, v.data(), v.size());
+    return p;
+}
+
+extern "C" {
+
+int32_t zkb_ctx_create(int32_t device, void* stream, zkb_ctx** out) {
+    if (!out) { g_last_error = "null output pointer"; return ZKB_ERR_INVALID; }
+    *out = nullptr;
+    zkb_ctx* c = new zkb_ctx();
+    try {
+        c->init(device, stream);
+    } catch (const InvalidArg& e) { g_last_error = e.what(); delete c; return ZKB_ERR_INVALID; }
+    catch (const std::exception& e) { g_last_error = e.what(); delete c; return ZKB_ERR_CUDA; }
+    *out = c;
+    return ZKB_OK;
+}
+void zkb_ctx_destroy(zkb_ctx* ctx) { if (ctx) { ctx->destroy(); delete ctx; } }
+const char* zkb_last_error(const zkb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+uint64_t zkb_kernel_launches(const zkb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int32_t zkb_last_stage_times(const zkb_ctx* ctx, zkb_stage_times* out) { if (!ctx || !out) return ZKB_ERR_INVALID; *out = ctx->times; return ZKB_OK; }
+void* zkb_host_alloc(size_t bytes) { void* p = nullptr; if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr; return p; }
+void zkb_host_free(void* p) { if (p) cudaFreeHost(p); }
+void zkb_free(void* p) { free(p); }
+
+int32_t zkb_prove(zkb_ctx* ctx, const zkb_air_desc* air, const uint8_t* const* cols, uint64_t force_nonce, uint8_t** proof_out,
+                  uint64_t* proof_len, zkb_transcript* transcript) {
+    return guarded(ctx, [&] {
+        if (!cols) throw InvalidArg("null trace columns");
+        std::vector<uint8_t> b = ctx->prove(air, cols, nullptr, force_nonce);
+        if (transcript) *transcript = ctx->ts;
+        if (proof_len) *proof_len = b.size();
+        if (proof_out) *proof_out = dup_bytes(b);
+    });
+}
+int32_t zkb_prove_device(zkb_ctx* ctx, const zkb_air_desc* air, const void* d_trace, uint64_t force_nonce, uint8_t** proof_out,
+                         uint64_t* proof_len, zkb_transcript* transcript) {
+    return guarded(ctx, [&] {
+        if (!d_trace) throw InvalidArg("null device trace");
+        std::vector<uint8_t> b = ctx->prove(air, nullptr, (const fe*)d_trace, force_nonce);
+        if (transcript) *transcript = ctx->ts;
+        if (proof_len) *proof_len = b.size();
+        if (proof_out) *proof_out = dup_bytes(b);
+    });
+}
+
+int32_t zkb_begin(zkb_ctx* ctx, const zkb_air_desc* air) { return guarded(ctx, [&] { ctx->begin(air); }); }
+int32_t zkb_trace_commit(zkb_ctx* ctx, const uint8_t* const* cols, uint8_t root_out[32]) { return guarded(ctx, [&] { ctx->trace_commit_host(cols, root_out); }); }
+int32_t zkb_trace_commit_device(zkb_ctx* ctx, const void* d, uint8_t root_out[32]) {
+    return guarded(ctx, [&] { if (!d) throw InvalidArg("null device trace"); ctx->trace_commit_device((const fe*)d, root_out); });
+}
+int32_t zkb_trace_read_frame(zkb_ctx* ctx, uint64_t lde_step, uint8_t* cur, uint8_t* nxt) {
+    return guarded(ctx, [&] {
+        if (ctx->stage < ST_TRACE) throw StateError("zkb_trace_read_frame: trace is not committed");
+        const uint64_t N = ctx->air.lde_size();
+        if (lde_step >= N || !cur || !nxt) throw InvalidArg("bad frame request");
+        std::vector<uint32_t> pos{(uint32_t)lde_step, (uint32_t)((lde_step + ctx->air.blowup) % N)};
+        const uint32_t w = ctx->air.w;
+        ctx->d_gather.ensure(1024 + 2 * (size_t)w * 16);
+        uint8_t* base = ctx->d_gather.as<uint8_t>();
+        ctx->h2d(base, pos.data(), 8);
+        k_gather_lde_rows<<<(2 * w + 127) / 128, 128, 0, ctx->stream>>>(ctx->lde_mat(), (const uint32_t*)base, 2, (fe*)(base + 1024));
+        ctx->check_launch();
+        std::vector<uint8_t> h(2 * (size_t)w * 16);
+        ctx->d2h(h.data(), base + 1024, h.size());
+        memcpy(cur, h.data(), (size_t)w * 16); memcpy(nxt, h.data() + (size_t)w * 16, (size_t)w * 16);
+    });
+}
+int32_t zkb_trace_polys_read(zkb_ctx* ctx, uint8_t* out) {
+    return guarded(ctx, [&] {
+        if (ctx->stage < ST_TRACE || ctx->stage >= ST_DEEP) throw StateError("zkb_trace_polys_read: trace polynomials are not available");
+        if (!out) throw InvalidArg("null output");
+        ctx->d2h(out, ctx->d_polys, (size_t)ctx->air.n * ctx->air.w * 16);
+    });
+}
+int32_t zkb_constraints_eval(zkb_ctx* ctx, const uint8_t alpha[16], uint8_t* evals_out) {
+    return guarded(ctx, [&] { if (!alpha) throw InvalidArg("null alpha"); ctx->constraints_eval(HF::reduce(HF::from_bytes(alpha).v), evals_out); });
+}
+int32_t zkb_constraints_commit(zkb_ctx* ctx, uint8_t root_out[32]) { return guarded(ctx, [&] { ctx->constraints_commit(root_out); }); }
+int32_t zkb_ood_eval(zkb_ctx* ctx, const uint8_t z[16], uint8_t* cur, uint8_t* nxt, uint8_t* h) {
+    return guarded(ctx, [&] {
+        if (!z) throw InvalidArg("null z");
+        ctx->ood_eval(HF::reduce(HF::from_bytes(z).v));
+        if (cur) memcpy(cur, ctx->ood_cur.data(), ctx->ood_cur.size() * 16);
+        if (nxt) memcpy(nxt, ctx->ood_next.data(), ctx->ood_next.size() * 16);
+        if (h) memcpy(h, ctx->ood_h.data(), ctx->ood_h.size() * 16);
+    });
+}
+int32_t zkb_deep_compose(zkb_ctx* ctx, const uint8_t a[16]) {
+    return guarded(ctx, [&] { if (!a) throw InvalidArg("null alpha"); ctx->deep_compose(HF::reduce(HF::from_bytes(a).v)); });
+}
+int32_t zkb_fri_num_layers(zkb_ctx* ctx, uint32_t* out) { return guarded(ctx, [&] { if (!out) throw InvalidArg("null output"); *out = ctx->fri_layers; }); }
+int32_t zkb_fri_commit_layer(zkb_ctx* ctx, uint8_t root_out[32]) { return guarded(ctx, [&] { ctx->fri_commit_layer(root_out); }); }
+int32_t zkb_fri_fold(zkb_ctx* ctx, const uint8_t a[16]) {
+    return guarded(ctx, [&] { if (!a) throw InvalidArg("null alpha"); ctx->fri_fold(HF::reduce(HF::from_bytes(a).v)); });
+}
+int32_t zkb_fri_remainder(zkb_ctx* ctx, uint8_t* coeffs_out, uint64_t* n_out, uint8_t commitment_out[32]) {
+    return guarded(ctx, [&] {
+        Digest32 d;
+        ctx->fri_remainder(&d);
+        if (coeffs_out) memcpy(coeffs_out, ctx->parts.remainder.data(), ctx->parts.remainder.size() * 16);
+        if (n_out) *n_out = ctx->parts.remainder.size();
+        if (commitment_out) memcpy(commitment_out, d.b, 32);
+    });
+}
+int32_t zkb_grind(zkb_ctx* ctx, const uint8_t seed[32], uint32_t bits, uint64_t* nonce_out) {
+    return guarded(ctx, [&] { if (!seed || !nonce_out) throw InvalidArg("null argument"); CK(cudaSetDevice(ctx->device)); *nonce_out = ctx->grind(seed, bits); });
+}
+int32_t zkb_query(zkb_ctx* ctx, uint32_t which, const uint32_t* positions, uint32_t n_pos, uint8_t* rows_out, uint8_t** proof_out,
+                  uint64_t* proof_len) {
+    return guarded(ctx, [&] {
+        if (ctx->stage < ST_FRI_DONE) throw StateError("zkb_query: the FRI commit phase is not finished");
+        if (!positions) throw InvalidArg("null positions");
+        std::vector<uint32_t> pos(positions, positions + n_pos);
+        std::vector<uint8_t> rows, paths;
+        ctx->query(which, pos, rows, paths);
+        if (rows_out) memcpy(rows_out, rows.data(), rows.size());
+        if (proof_len) *proof_len = paths.size();
+        if (proof_out) *proof_out = dup_bytes(paths);
+    });
+}
+
+int32_t zkb_mimc_trace_device(zkb_ctx* ctx, const uint8_t* seeds, uint32_t w, uint64_t n, const uint8_t* rc, uint32_t n_rc, void** d_out) {
+    return guarded(ctx, [&] {
+        if (!seeds || !rc || !d_out || w == 0 || n == 0 || !is_pow2(n_rc)) throw InvalidArg("bad mimc trace request");
+        CK(cudaSetDevice(ctx->device));
+        ctx->d_user_trace.ensure((size_t)w * n * 16);
+        ctx->d_aux.ensure(((size_t)w + n_rc) * 16);
+        ctx->h2d(ctx->d_aux.p, seeds, (size_t)w * 16);
+        ctx->h2d(ctx->d_aux.as<fe>() + w, rc, (size_t)n_rc * 16);
+        k_mimc_trace<<<(w + 31) / 32, 32, 0, ctx->stream>>>(ctx->d_aux.as<fe>(), w, n, ctx->d_aux.as<fe>() + w, n_rc, ctx->d_user_trace.as<fe>());
+        ctx->check_launch();
+        CK(cudaStreamSynchronize(ctx->stream));
+        *d_out = ctx->d_user_trace.p;
+    });
+}
+int32_t zkb_mimc_trace(zkb_ctx* ctx, const uint8_t* seeds, uint32_t w, uint64_t n, const uint8_t* rc, uint32_t n_rc, uint8_t* out) {
+    void* d = nullptr;
+    int32_t r = zkb_mimc_trace_device(ctx, seeds, w, n, rc, n_rc, &d);
+    if (r != ZKB_OK) return r;
+    return guarded(ctx, [&] { if (!out) throw InvalidArg("null output"); ctx->d2h(out, d, (size_t)w * n * 16); });
+}
+int32_t zkb_upload_trace(zkb_ctx* ctx, const uint8_t* const* cols, uint32_t w, uint64_t n, void** d_out) {
+    return guarded(ctx, [&] {
+        if (!d_out) throw InvalidArg("null output");
+        CK(cudaSetDevice(ctx->device));
+        *d_out = (void*)ctx->upload_cols(cols, w, n, ctx->d_user_trace);
+        CK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int32_t zkb_test_field(zkb_ctx* ctx, const uint8_t* a, const uint8_t* b, uint32_t n, uint8_t* mul, uint8_t* add, uint8_t* sub, uint8_t* inv) {
+    return guarded(ctx, [&] {
+        CK(cudaSetDevice(ctx->device));
+        ctx->d_aux.ensure((size_t)n * 16 * 6);
+        fe* base = ctx->d_aux.as<fe>();
+        ctx->h2d(base, a, (size_t)n * 16); ctx->h2d(base + n, b, (size_t)n * 16);
+        k_test_field<<<(n + 127) / 128, 128, 0, ctx->stream>>>(base, base + n, base + 2 * (size_t)n, base + 3 * (size_t)n, base + 4 * (size_t)n, base + 5 * (size_t)n, n);
+        ctx->check_launch();
+        ctx->d2h(mul, base + 2 * (size_t)n, (size_t)n * 16); ctx->d2h(add, base + 3 * (size_t)n, (size_t)n * 16);
+        ctx->d2h(sub, base + 4 * (size_t)n, (size_t)n * 16); ctx->d2h(inv, base + 5 * (size_t)n, (size_t)n * 16);
+    });
+}
+int32_t zkb_test_hash_elements(zkb_ctx* ctx, const uint8_t* rows, uint32_t count, uint32_t n_rows, uint8_t* out) {
+    return guarded(ctx, [&] {
+        CK(cudaSetDevice(ctx->device));
+        size_t in_bytes = (size_t)count * n_rows * 16;
+        ctx->d_aux.ensure(in_bytes + 16 + (size_t)n_rows * 32);
+        uint8_t* base = ctx->d_aux.as<uint8_t>();
+        size_t o = ((in_bytes + 15) / 16) * 16;
+        if (in_bytes) ctx->h2d(base, rows, in_bytes);
+        k_test_hash<<<(n_rows + 127) / 128, 128, 0, ctx->stream>>>((const fe*)base, count, n_rows, (uint32_t*)(base + o));
+        ctx->check_launch();
+        ctx->d2h(out, base + o, (size_t)n_rows * 32);
+    });
+}
+int32_t zkb_test_merkle_root(zkb_ctx* ctx, const uint8_t* leaves, uint64_t n, uint8_t root_out[32]) {
+    return guarded(ctx, [&] {
+        if (n < 2 || !is_pow2(n)) throw InvalidArg("leaf count must be a power of two >= 2");
+        CK(cudaSetDevice(ctx->device));
+        ctx->d_aux.ensure(2 * n * 32);
+        ctx->h2d(ctx->d_aux.as<uint8_t>() + n * 32, leaves, n * 32);
+        ctx->build_merkle(ctx->d_aux.as<uint32_t>(), n);
+        ctx->d2h(root_out, ctx->d_aux.as<uint8_t>() + 32, 32);
+    });
+}
+int32_t zkb_test_lde(zkb_ctx* ctx, const uint8_t* const* cols, uint32_t w, uint64_t n, uint32_t blowup, uint8_t* polys_out, uint8_t* lde_out) {
+    return guarded(ctx, [&] {
+        // drive K1+K2 through a throw-away training-shaped description
+        std::vector<uint8_t> zero(16, 0);
+        uint32_t col = 0; uint64_t step = 0;
+        zkb_air_desc d{};
+        d.air_id = ZKB_AIR_ID_TRAINING; d.trace_width = w; d.trace_len = n; d.num_queries = 1; d.blowup = blowup; d.grinding_bits = 0;
+        d.field_extension = 1; d.folding = 16; d.rem_max_degree = 7; d.batching_constraints = 1; d.batching_deep = 1;
+        d.assert_cols = &col; d.assert_steps = &step; d.assert_values = zero.data(); d.n_assertions = 1;
+        ctx->begin(&d);
+        uint8_t root[32];
+        ctx->trace_commit_host(cols, root);
+        if (polys_out) ctx->d2h(polys_out, ctx->d_polys, (size_t)n * w * 16);
+        if (lde_out) {
+            const uint64_t N = n * blowup;
+            std::vector<uint32_t> pos;
+            // gather in slices of 128 rows to reuse the query gather kernel
+            ctx->d_gather.ensure(1024 + (size_t)128 * w * 16);
+            uint8_t* base = ctx->d_gather.as<uint8_t>();
+            for (uint64_t r0 = 0; r0 < N; r0 += 128) {
+                uint32_t cnt = (uint32_t)std::min<uint64_t>(128, N - r0);
+                pos.resize(cnt);
+                for (uint32_t q = 0; q < cnt; q++) pos[q] = (uint32_t)(r0 + q);
+                ctx->h2d(base, pos.data(), cnt * 4);
+                k_gather_lde_rows<<<(cnt * w + 127) / 128, 128, 0, ctx->stream>>>(ctx->lde_mat(), (const uint32_t*)base, cnt, (fe*)(base + 1024));
+                ctx->check_launch();
+                ctx->d2h(lde_out + r0 * w * 16, base + 1024, (size_t)cnt * w * 16);
+            }
+        }
+        ctx->stage = ST_IDLE;
+    });
+}
+
+}  // extern "C"
