@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Headline benchmark: STARK proofs per second (and ms per proof) for the reference's proving path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl zkb200|reference]
+
+A step is one complete proof (`Prover::prove`, /root/reference src/main.rs:228) of a seeded synthetic trace.
+`value` times it with the trace already resident in HBM, `e2e` through the C ABI with pinned HOST columns
+(H2D of the trace and D2H of the proof inside the timed region).  Multi-GPU runs one independent proof stream
+per rank (weak scaling, no collective on the data path).  `--impl reference` times the CPU oracle — the
+restatement of the reference's Winterfell CPU prover (the Rust original cannot be built in this image) —
+on all host cores, on the same workload.  Prints exactly one JSON line (rank 0)."""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (air, n, w, blowup, description)
+    "training_2p16": ("training", 1 << 16, 240, 16, "training AIR (src/training), 2^16-row x 240-col trace, blowup 16 (LDE 2^20 rows)"),
+    "training_8192": ("training", 8192, 240, 16, "training AIR, 8192-row trace (bs=50, the CLI maximum), blowup 16"),
+    "training_2p18": ("training", 1 << 18, 240, 16, "training-shaped AIR, 2^18-row x 240-col trace, blowup 16"),
+    "training_2p20": ("training", 1 << 20, 240, 16, "training-shaped AIR, 2^20-row x 240-col trace, blowup 16 (LDE 60 GiB)"),
+    "mimc_2p14": ("mimc", 1 << 14, 64, 8, "MiMC chains, 2^14 steps x 64 columns, blowup 8"),
+    "mimc_2p20": ("mimc", 1 << 20, 64, 8, "MiMC chains, 2^20 steps x 64 columns, blowup 8 (LDE 8 GiB)"),
+    "aggregation_16": ("aggregation", 32, 120, 16, "FedAvg aggregation AIR over 16 updates, 32 x 120 trace"),
+}
+
+
+def algorithmic_bytes(n, w, beta, ce, c, folding=16, rem_domain=128):
+    """compulsory HBM traffic per proof, stage by stage."""
+    s, N = 16, n * beta
+    b = {
+        "interp": 2 * w * n * s,
+        "lde": w * n * s + w * N * s,
+        "leaf": w * N * s + 32 * N,
+        "merkle": 96 * N,
+        "ceval": w * (ce * n) * s + ce * n * s,
+        "comp": 2 * ce * n * s + c * n * s + c * N * s + (c * N * s + 32 * N) + 96 * N,
+        "ood": (w + c) * n * s,
+        "deep": (w + c) * n * s + n * s + (n * s + N * s),
+    }
+    fri, m = 0, N
+    while m > rem_domain:
+        fri += m * s + (m // folding) * s + 32 * m // folding + 96 * m // folding
+        m //= folding
+    b["fri"] = fri
+    b["total"] = sum(b.values())
+    return b
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.samples, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        rows = [r for t, r in self.samples if t0 <= t <= t1 and len(r) >= 7] or [r for _, r in self.samples if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        try:
+            sm = [float(r[0]) for r in rows]
+            reasons = []
+            for idx, name in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap")):
+                if any(r[idx].lower().startswith("active") for r in rows):
+                    reasons.append(name)
+            return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows),
+                    "samples": len(rows), "reasons": reasons}
+        except ValueError:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unparsed"]}
+
+
+def build_workload(name, seed):
+    """Returns (air description, trace array (w, n, 2) uint64 or None when generated on the device, extra)."""
+    import zk_stark_project_b200 as Z
+    from zk_stark_project_b200 import synthetic as S
+    kind, n, w, beta, _ = WORKLOADS[name]
+    opts = Z.ProofOptions(40, beta, 21, Z.FieldExtension.NONE, 16, 7)  # src/main.rs:98-107 (MiMC: blowup 8 per BASELINE.json)
+    if kind == "training":
+        data = S.random_felts(w * n, seed).reshape(w, n, 2)
+        return S.synthetic_training_air(n, opts, data), data, opts
+    if kind == "aggregation":
+        import random
+        from zk_stark_project_b200 import field as F
+        rng = random.Random(seed)
+        mk = lambda sig: F.f64_to_signed_felt(rng.gauss(0, sig), 1e6)[0]
+        gw = [[mk(1e4) for _ in range(9)] for _ in range(6)]
+        gb = [mk(1e4) for _ in range(6)]
+        reps = [rng.randrange(2**64) for _ in range(16)]
+        lw = [[[Z.f64_to_felt(r / 1e6)] * 9 for _ in range(6)] for r in reps]
+        lb = [[Z.f64_to_felt(r / 1e6)] * 6 for r in reps]
+        p = Z.GlobalUpdateProver(opts, gw, gb, lw, lb, Z.f64_to_felt(16.0), seed=seed)
+        tr = p.build_trace()
+        return p.describe(tr), np.ascontiguousarray(tr.data), opts
+    # mimc: the chain trace is produced by the caller-side generator (device kernel for the product, oracle for the reference)
+    return None, None, opts
+
+
+def mimc_air(opts, w, n, first, last):
+    import zk_stark_project_b200 as Z
+    pub = Z.MimcInputs(first, last)
+    return Z.MimcAir(w, n, pub, opts).describe()
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle prover (restatement of Winterfell's CPU prover) on all host cores."""
+    if rank != 0:
+        return
+    from oracle import pyoracle as O
+    import zk_stark_project_b200 as Z
+    O.build()
+    cores = os.cpu_count() or 1
+    O.set_threads(cores)
+    kind, n, w, beta, desc = WORKLOADS[args.workload]
+    air, data, opts = build_workload(args.workload, 0x5EED0000)
+    if kind == "mimc":
+        rc = Z.get_round_constants()
+        raw = O.mimc_trace([j + 1 for j in range(w)], n, rc)
+        data = np.frombuffer(raw, dtype=np.uint64).reshape(w, n, 2)
+        get = lambda c, r: int(data[c, r, 0]) | (int(data[c, r, 1]) << 64)
+        air = mimc_air(opts, w, n, [get(j, 0) for j in range(w)], [get(j, n - 1) for j in range(w)])
+    tb = data.tobytes()
+    for _ in range(args.warmup):
+        O.prove(air, tb)
+    t0 = time.time()
+    for _ in range(args.steps):
+        O.prove(air, tb)
+    dt = (time.time() - t0) / args.steps
+    val = 1.0 / dt
+    line = {
+        "impl": "reference", "metric": "stark_proofs_per_sec", "value": val, "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u128 mod p (f128 field), u32 BLAKE3", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "options": "40 queries, grinding 21, FRI folding 16, remainder degree <= 7"},
+        "cpu_baseline": {"value": val, "unit": "proofs/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full proofs of the workload (C++ restatement of Winterfell 0.12's CPU prover; "
+                                   "the Rust reference itself cannot be built in this image: no cargo/rustc)"},
+        "e2e": {"value": val, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="training_2p16", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="zkb200", choices=["zkb200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle timing at N=1")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import zk_stark_project_b200 as Z
+    from zk_stark_project_b200 import lib as L
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the zkb200 proving path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    kind, n, w, beta, desc = WORKLOADS[args.workload]
+    ctx = L.Context(local_rank)  # default stream: the same stream torch.cuda.Event records on
+    air, data, opts = build_workload(args.workload, 0x5EED0000 + rank)
+    nbytes = w * n * 16
+    pinned = L.PinnedBuffer(nbytes)
+    if kind == "mimc":
+        rc = Z.get_round_constants()
+        raw = ctx.mimc_trace([j + 1 + 1000 * rank for j in range(w)], n, rc)  # device-side chain generator
+        data = np.frombuffer(raw, dtype=np.uint64).reshape(w, n, 2)
+        get = lambda c, r: int(data[c, r, 0]) | (int(data[c, r, 1]) << 64)
+        air = mimc_air(opts, w, n, [get(j, 0) for j in range(w)], [get(j, n - 1) for j in range(w)])
+    pinned.view()[:] = np.frombuffer(data.tobytes(), dtype=np.uint8) if kind == "mimc" else data.reshape(-1).view(np.uint8)
+    d_trace = ctx.upload_trace(pinned.ptr, w, n)
+    air_dict, air = air, ctx.prepare(air)  # marshal the AIR description once, outside the timed regions
+
+    ce = 8 if kind == "mimc" else 2
+    c = 6 if kind == "mimc" else 1
+    alg = algorithmic_bytes(n, w, beta, ce, c)
+
+    # ---- device-resident arm (`value`) ----------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        ctx.prove_device(air, d_trace)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    stage_acc = {}
+    barrier()
+    l0 = ctx.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        proof, ts = ctx.prove_device(air, d_trace)
+        for k_, v_ in ctx.stage_times().items():
+            stage_acc[k_] = stage_acc.get(k_, 0.0) + v_
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = ctx.launches() - l0
+    ms = e0.elapsed_time(e1)
+    # ---- end-to-end arm: host columns in pinned memory through zkb_prove ---------------------------------------------
+    for _ in range(min(args.warmup, 2)):
+        ctx.prove_host(air, pinned.ptr)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        proof_e2e, _ = ctx.prove_host(air, pinned.ptr)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    sampler.stop()
+    assert proof_e2e == proof, "e2e proof differs from the device-resident proof"
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt[0])
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+        stages = {k_: v_ / args.steps for k_, v_ in stage_acc.items()}
+        lde_ms = max(stages.get("lde", 0.0), 1e-6)
+        achieved = alg["lde"] / (lde_ms * 1e-3) / 1e9
+        # per-stage achieved bandwidth against the same peak, for the profile notes
+        per_stage = {}
+        for st, key in (("interpolate", "interp"), ("lde", "lde"), ("leaf_hash", "leaf"), ("merkle", "merkle"), ("constraints", "ceval"),
+                        ("composition", "comp"), ("ood", "ood"), ("deep", "deep"), ("fri", "fri")):
+            t_ms = stages.get(st, 0.0)
+            per_stage[st] = {"ms": round(t_ms, 4), "alg_GB": round(alg[key] / 1e9, 4),
+                             "GBps": round(alg[key] / (t_ms * 1e-3) / 1e9, 1) if t_ms > 0 else None}
+        per_stage["grind"] = {"ms": round(stages.get("grind", 0.0), 4)}
+        per_stage["queries"] = {"ms": round(stages.get("queries", 0.0), 4)}
+        line = {
+            "metric": "stark_proofs_per_sec", "value": world * args.steps / (ms * 1e-3), "unit": "proofs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u128 mod p (f128 field, 4x u32 limbs), u32 BLAKE3", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "options": "40 queries, grinding 21, FRI folding 16, remainder degree <= 7",
+                       "proofs_per_gpu_per_step": 1, "l2": "inputs larger than L2 (trace %d MiB, LDE %d MiB)" % (nbytes >> 20, (nbytes * beta) >> 20),
+                       "proof_bytes": len(proof), "parallelism": f"{world} independent proof stream(s), one per GPU, no data-path collective"},
+            "prove_ms": ms / args.steps,
+            "roofline": {"bound": "hbm", "kernel": "k_ntt_pass (coset LDE, K2)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_proof": alg["lde"], "kernel_ms_per_proof": lde_ms,
+                         "note": "integer-ALU bound: a radix-2 f128 butterfly is ~105 SASS integer instructions per 32 bytes moved"},
+            "proof_roofline": {"algorithmic_bytes": alg["total"], "t_hbm_ms": alg["total"] / peak / 1e6,
+                               "frac": (alg["total"] / peak / 1e6) / (ms / args.steps)},
+            "stages": per_stage,
+            "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "proofs/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": len(proof)},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(t_wall0, t_wall1),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import pyoracle as O
+            O.build()
+            cores = os.cpu_count() or 1
+            O.set_threads(cores)
+            tb = bytes(pinned.view())
+            t0 = time.time()
+            ref, ts_ref, secs = O.prove(air_dict, tb)
+            dt = time.time() - t0
+            line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "proofs/s", "ms_per_proof": dt * 1e3, "cores": cores, "kind": "port",
+                                    "sample": "1 full proof of the same workload (C++ restatement of Winterfell's CPU prover, all host cores)",
+                                    "proof_identical_to_gpu": ref == proof}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

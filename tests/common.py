@@ -23,12 +23,7 @@ def splitmix(seed):
     return nxt
 
 
-def random_felts(count, seed):
-    """uniform-ish elements below p as a (count, 2) uint64 array (hi word < 2^64 - 1 keeps them canonical)."""
-    rng = np.random.default_rng(seed)
-    a = rng.integers(0, 1 << 64, size=(count, 2), dtype=np.uint64)
-    a[:, 1] &= np.uint64(0x7FFFFFFFFFFFFFFF)
-    return a
+from zk_stark_project_b200.synthetic import random_felts, synthetic_training_air  # noqa: E402,F401
 
 
 def options(blowup=16, queries=40, grinding=8):
@@ -63,22 +58,6 @@ def aggregation_prover(num_updates, opts, seed=0x5EED0003):
 
 def mimc_prover(width, steps, opts):
     return Z.MimcProver(opts, [j + 1 for j in range(width)], steps)
-
-
-def synthetic_training_air(n, opts, data):
-    """Training-shaped AIR over an arbitrary 240-column trace (the prover is data-oblivious):
-    `data` is the (240, n, 2) uint64 trace; batch_size chosen so the reference would pick this trace length."""
-    w = data.shape[0]
-    half = w // 2
-    get = lambda c, r: int(data[c, r, 0]) | (int(data[c, r, 1]) << 64)
-    bs = max(1, n // (2 * 60)) if n > 16 else 1
-    while max(1 << (2 * 60 * bs - 1).bit_length(), 16) > n and bs > 1:
-        bs -= 1
-    x = [[Z.f64_to_felt((i + j) * 0.1) for j in range(FE)] for i in range(bs)]
-    y = [[Z.f64_to_felt(1.0) if a == i % AC else 0 for a in range(AC)] for i in range(bs)]
-    pub = Z.TrainingUpdateInputs([get(c, 0) for c in range(half)], [get(c, n - 1) for c in range(half)], n - 1, x, y,
-                                 Z.f64_to_felt(0.01), Z.f64_to_felt(1e6), bs)
-    return Z.TrainingUpdateAir(w, n, pub, opts).describe()
 
 
 TS_FIELDS = ["trace_root", "constraint_alpha", "constraint_root", "z", "deep_alpha", "n_fri_layers", "fri_roots", "fri_alphas",

@@ -89,15 +89,59 @@ struct NttPass {
 
 __device__ __forceinline__ uint32_t bitrev(uint32_t v, uint32_t bits) { return bits == 0 ? 0u : (__brev(v) >> (32 - bits)); }
 
-__global__ void __launch_bounds__(256) k_ntt_pass(const NttPass p) {
+// RHO consecutive DIT layers (lam0, lam0 + RHO] of one column, done in registers: the 2^RHO elements of a unit sit at
+// positions base + d * 2^lam0.  Layer lam uses tw[2^(lam-1) - 1 + (p0 mod 2^(lam-1))] for the pair (p0, p0 + 2^(lam-1)).
+template <int RHO>
+__device__ __forceinline__ void ntt_unit(fe* __restrict__ col, const uint32_t rs, const fe* __restrict__ tw,
+                                         const uint32_t base, const uint32_t lam0) {
+    constexpr int R = 1 << RHO;
+    fe x[R];
+    const uint32_t step = rs << lam0;
+    fe* p = col + base * rs;
+#pragma unroll
+    for (int d = 0; d < R; d++) x[d] = p[d * step];
+    const uint32_t base_low = base & ((1u << lam0) - 1u);
+#pragma unroll
+    for (int s = 0; s < RHO; s++) {
+        const fe* twl = tw + ((1u << (lam0 + s)) - 1u) + base_low;
+#pragma unroll
+        for (int t = 0; t < (1 << s); t++) {
+            const fe w = twl[(uint32_t)t << lam0];
+#pragma unroll
+            for (int g = 0; g < (R >> (s + 1)); g++) {
+                const int d0 = g * (2 << s) + t, d1 = d0 + (1 << s);
+                const fe u = x[d0];
+                const fe v = fe_mul(x[d1], w);
+                x[d0] = fe_add(u, v);
+                x[d1] = fe_sub(u, v);
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < R; d++) p[d * step] = x[d];
+}
+
+template <int RHO>
+__device__ __forceinline__ void ntt_round(fe* sm, const fe* tw, uint32_t rs, uint32_t log_cj, uint32_t logS, uint32_t lam0) {
+    const uint32_t cj_mask = (1u << log_cj) - 1u;
+    const uint32_t units = (1u << (logS - RHO)) << log_cj;
+    for (uint32_t idx = threadIdx.x; idx < units; idx += blockDim.x) {
+        const uint32_t jj = idx & cj_mask, u = idx >> log_cj;
+        const uint32_t base = (u & ((1u << lam0) - 1u)) + ((u >> lam0) << (lam0 + RHO));
+        ntt_unit<RHO>(sm + jj, rs, tw, base, lam0);
+    }
+}
+
+__global__ void __launch_bounds__(256, 3) k_ntt_pass(const NttPass p) {
     extern __shared__ uint4 smem_raw[];
     fe* sm = reinterpret_cast<fe*>(smem_raw);
     const uint32_t logS = p.b - p.a, S = 1u << logS, cj = p.cj;
+    const uint32_t log_cj = 31 - __clz(cj);
     const uint32_t rs = cj + (cj > 1 ? 1u : 0u);  // padded row stride: conflict-free column reads
     fe* tw = sm + (size_t)S * rs;
 
     // tile coordinates: column tile fastest, then coset (so one input tile is reused out of L2), then (t_low, u0)
-    const uint32_t n_ct = (p.ncols + cj - 1) / cj;
+    const uint32_t n_ct = (p.ncols + cj - 1) >> log_cj;
     uint32_t id = blockIdx.x;
     const uint32_t ct = id % n_ct; id /= n_ct;
     const uint32_t kk = id % p.n_cosets; id /= p.n_cosets;
@@ -123,52 +167,45 @@ __global__ void __launch_bounds__(256) k_ntt_pass(const NttPass p) {
         tw[q] = t;
     }
     // load: row v of the tile is input row (u0 + (n/2^b) v) * 2^a + t_low; store bit-reversed
-    const uint32_t c_base = ct * cj;
-    const uint32_t E = S * cj;
-    for (uint32_t idx = threadIdx.x; idx < E; idx += blockDim.x) {
-        const uint32_t v = idx / cj, jj = idx - v * cj;
-        const size_t row = (((size_t)u0 + ((size_t)v << (p.log_n - p.b))) << p.a) + t_low;
-        fe x = fe_zero();
-        if (c_base + jj < p.ncols) x = fe_load(in + row * p.w_in + p.col0_in + c_base + jj);
-        sm[bitrev(v, logS) * rs + jj] = x;
+    const uint32_t c_base = ct << log_cj;
+    const uint32_t E = S << log_cj;
+    {
+        const fe* src = in + (((size_t)u0 << p.a) + t_low) * p.w_in + p.col0_in + c_base;
+        const size_t vstride = ((size_t)p.w_in << (p.log_n - p.b)) << p.a;
+        for (uint32_t idx = threadIdx.x; idx < E; idx += blockDim.x) {
+            const uint32_t v = idx >> log_cj, jj = idx & (cj - 1u);
+            fe x = fe_zero();
+            if (c_base + jj < p.ncols) x = fe_load(src + (size_t)v * vstride + jj);
+            sm[bitrev(v, logS) * rs + jj] = x;
+        }
     }
     __syncthreads();
-    // butterflies
-    const uint32_t nb = (S >> 1) * cj;
-    for (uint32_t lam = 1; lam <= logS; lam++) {
-        const uint32_t half = 1u << (lam - 1);
-        for (uint32_t bidx = threadIdx.x; bidx < nb; bidx += blockDim.x) {
-            const uint32_t q = bidx / cj, jj = bidx - q * cj;
-            const uint32_t th = q & (half - 1u);
-            const uint32_t p0 = ((q >> (lam - 1)) << lam) + th;
-            fe* x0 = sm + p0 * rs + jj;
-            fe* x1 = x0 + half * rs;
-            const fe u = *x0;
-            const fe v = fe_mul(*x1, tw[half - 1u + th]);
-            *x0 = fe_add(u, v);
-            *x1 = fe_sub(u, v);
-        }
+    // butterflies: rounds of up to three layers held in registers
+    for (uint32_t lam0 = 0; lam0 < logS;) {
+        const uint32_t left = logS - lam0;
+        if (left >= 3 && left != 4) { ntt_round<3>(sm, tw, rs, log_cj, logS, lam0); lam0 += 3; }
+        else if (left >= 2) { ntt_round<2>(sm, tw, rs, log_cj, logS, lam0); lam0 += 2; }
+        else { ntt_round<1>(sm, tw, rs, log_cj, logS, lam0); lam0 += 1; }
         __syncthreads();
     }
     // store
     if (p.out_panel) {
         // panel = k*2^a + t_low, slot = t_high; consecutive threads write consecutive slots of one column
         const size_t panel = ((size_t)k << p.a) + t_low;
+        fe* dst = p.out + ((panel * p.w_out + p.col0_out + c_base) << logS);
         for (uint32_t idx = threadIdx.x; idx < E; idx += blockDim.x) {
             const uint32_t jj = idx >> logS, th = idx & (S - 1u);
-            if (c_base + jj < p.ncols) {
-                fe x = sm[th * rs + jj];
-                fe_store(p.out + ((panel * p.w_out + p.col0_out + c_base + jj) << logS) + th, x);
-            }
+            if (c_base + jj < p.ncols) fe_store(dst + ((size_t)jj << logS) + th, sm[th * rs + jj]);
         }
     } else {
+        fe* dst = out + (((size_t)u0 << p.b) + t_low) * p.w_out + p.col0_out + c_base;
+        const size_t tstride = (size_t)p.w_out << p.a;
         for (uint32_t idx = threadIdx.x; idx < E; idx += blockDim.x) {
-            const uint32_t th = idx / cj, jj = idx - th * cj;
+            const uint32_t th = idx >> log_cj, jj = idx & (cj - 1u);
             if (c_base + jj < p.ncols) {
                 fe x = sm[th * rs + jj];
                 if (p.do_scale) x = fe_mul(x, p.scale);
-                const size_t row = ((size_t)u0 << p.b) + t_low + ((size_t)th << p.a);
-                fe_store(out + row * p.w_out + p.col0_out + c_base + jj, x);
+                fe_store(dst + (size_t)th * tstride + jj, x);
             }
         }
     }

@@ -150,18 +150,23 @@ class Context:
     def _col_ptrs(self, trace_ptr, w, n):
         return (C.c_void_p * w)(*[trace_ptr + j * n * 16 for j in range(w)])
 
+    @staticmethod
+    def prepare(air):
+        """Marshal an AIR description once (the Rust glue would hold this struct ready-made)."""
+        return air if isinstance(air, AirDesc) else make_desc(air)
+
     def prove_host(self, air, trace_ptr, force_nonce=0):
         """trace_ptr: host address of a column-major [w][n] trace."""
-        d = make_desc(air)
+        d = self.prepare(air)
         out, ln, ts = C.c_void_p(), C.c_uint64(), Transcript()
-        cols = self._col_ptrs(trace_ptr, air["trace_width"], air["trace_len"])
+        cols = self._col_ptrs(trace_ptr, d.trace_width, d.trace_len)
         self.check(self.lib.zkb_prove(self.handle, C.byref(d), cols, C.c_uint64(force_nonce), C.byref(out), C.byref(ln), C.byref(ts)))
         proof = C.string_at(out, ln.value)
         self.lib.zkb_free(out)
         return proof, ts
 
     def prove_device(self, air, d_trace, force_nonce=0):
-        d = make_desc(air)
+        d = self.prepare(air)
         out, ln, ts = C.c_void_p(), C.c_uint64(), Transcript()
         self.check(self.lib.zkb_prove_device(self.handle, C.byref(d), C.c_void_p(d_trace), C.c_uint64(force_nonce), C.byref(out),
                                              C.byref(ln), C.byref(ts)))
