@@ -1,0 +1,138 @@
+"""CPU: the Python mirror of the reference's host-side code, following the reference's own unit tests
+(src/helper.rs:414-689, tests/simple_check.rs) and its trace-shape rules."""
+import math
+
+import numpy as np
+import pytest
+
+import zk_stark_project_b200 as Z
+from zk_stark_project_b200 import field as F
+from zk_stark_project_b200.training import AC, FE
+from tests import common as T
+
+P = Z.P
+
+
+def test_constants():
+    """tests/simple_check.rs:33-41."""
+    assert (AC, FE) == (6, 9)
+    assert Z.f64_to_felt(1.5) == 1500000 and Z.f64_to_felt(0.0) == 0
+    assert Z.get_round_constants()[0] == 10**6 and len(Z.get_round_constants()) == 64
+
+
+def test_signed_ops_with_sign_zero_are_plain_field_ops():
+    """src/helper.rs:425-467."""
+    a, b = 123456789, 987654
+    assert F.add(a, b, 0, 0) == ((a + b) % P, 0)
+    assert F.multiply(a, b, 0, 0) == (a * b % P, 0)
+    assert F.divide(a, b, 0, 0) == (a * pow(b, P - 2, P) % P, 0)
+    # sub_generic(a, 0, b, 0) = add_generic(a, 0, b, 1): with exactly one negative operand the "wrapped" branch is not
+    # taken (src/signed.rs:17-31), so the value is a + b and the sign bit s_a*s_b = 0
+    assert F.subtract(a, b, 0, 0) == ((a + b) % P, 0)
+
+
+def test_encode_signed_round_trip():
+    v, s = F.encode_signed(5)
+    assert (v, s) == (5, 0)
+    v, s = F.encode_signed(-5)
+    assert s == 1 and v == F.Felt((2**128 - 5) & (2**128 - 1))
+    assert F.cleanse(v, s) == (F.MAX - v + 1) % P == 5  # cleanse recovers |x| for negative encodings
+
+
+def test_f64_round_half_away_from_zero():
+    assert F._rust_round(0.5) == 1 and F._rust_round(2.5) == 3 and F._rust_round(-0.5) == -1
+
+
+def test_transpose_and_trace_table():
+    """src/helper.rs:482-496 and TraceTable::init limits."""
+    rows = [[r * 10 + c for c in range(3)] for r in range(8)]
+    t = Z.TraceTable.from_rows(rows)
+    assert (t.width(), t.length()) == (3, 8) and t.get(2, 5) == 52 and t.column(1) == [r * 10 + 1 for r in range(8)]
+    with pytest.raises(ValueError):
+        Z.TraceTable.from_rows([[1, 2]] * 6)  # length not a power of two
+    with pytest.raises(ValueError):
+        Z.TraceTable(np.zeros((256, 8, 2), dtype=np.uint64))  # too wide
+
+
+def test_proof_options_validation():
+    o = Z.ProofOptions.reference()
+    assert (o.num_queries, o.blowup_factor, o.grinding_factor, o.fri_folding_factor, o.fri_remainder_max_degree) == (40, 16, 21, 16, 7)
+    for bad in (dict(num_queries=0), dict(blowup_factor=3), dict(grinding_factor=33), dict(fri_folding_factor=5), dict(fri_remainder_max_degree=6)):
+        kw = dict(num_queries=40, blowup_factor=16, grinding_factor=21, field_extension=1, fri_folding_factor=16, fri_remainder_max_degree=7)
+        kw.update(bad)
+        with pytest.raises(ValueError):
+            Z.ProofOptions(**kw)
+
+
+def test_training_trace_shape_and_public_inputs():
+    """src/training/prover.rs:63-65,128-130,245-246; src/training/air.rs:75-89."""
+    for bs, n in ((1, 128), (2, 256), (5, 1024)):
+        p = T.training_prover(bs, T.options())
+        assert p.trace_length == n
+        tr = p.build_trace()
+        assert (tr.width(), tr.length()) == (240, n)
+        # masked = raw + mask: column j minus column j+120 is the raw state, constant once the batch is consumed
+        raw_last = [(tr.get(j, n - 1) - tr.get(j + 120, n - 1)) % P for j in range(120)]
+        raw_prev = [(tr.get(j, n - 2) - tr.get(j + 120, n - 2)) % P for j in range(120)]
+        assert raw_last == raw_prev
+        assert all(tr.get(j + 120, 5) < 2**64 for j in range(120))
+        pub = p.get_pub_inputs(tr)
+        assert len(pub.to_elements()) == 244 + 15 * bs
+        assert pub.to_elements()[240] == Z.f64_to_felt(float(n - 1))
+        air = p.describe(tr)
+        assert len(air["assertions"]) == 240 and air["assertions"][120] == (0, n - 1, tr.get(0, n - 1))
+
+
+def test_training_step_matches_f64_reference():
+    """src/helper.rs:580-689: one SGD step in sign-encoded fixed point tracks an f64 implementation."""
+    from zk_stark_project_b200.training import backward_propagation_layer, forward_propagation_layer, mse_prime
+    pr, lr = Z.f64_to_felt(1e6), Z.f64_to_felt(0.01)  # pr = 1e12 as a felt, lr = 1e4
+    wf = [[0.1 * (i + 1) - 0.05 * j for j in range(FE)] for i in range(AC)]
+    bf = [0.01 * i for i in range(AC)]
+    xf = [0.1 * j for j in range(FE)]
+    yf = [1.0 if i == 2 else 0.0 for i in range(AC)]
+    enc = lambda v: F.f64_to_signed_felt(v, 1e6)
+    w, ws = [[enc(v)[0] for v in r] for r in wf], [[enc(v)[1] for v in r] for r in wf]
+    b, bs = [enc(v)[0] for v in bf], [enc(v)[1] for v in bf]
+    x, xs = [enc(v)[0] for v in xf], [enc(v)[1] for v in xf]
+    y = [Z.f64_to_felt(v) for v in yf]
+    out, out_s = forward_propagation_layer(w, b, x, ws, bs, xs, pr)
+    dec = lambda v, s: (-(F.cleanse(v, s)) if s else v) / 1e6
+    out_f = [sum(wf[i][j] * xf[j] for j in range(FE)) + bf[i] for i in range(AC)]
+    # the reference divides by pr = f64_to_felt(1e6) = 1e12 in the field (exact division is not integer division), so only the
+    # structure is checked here: signs are bits and outputs are field elements
+    assert all(s in (0, 1) for s in out_s) and all(0 <= v < P for v in out)
+    err, err_s = mse_prime(y, out, out_s, pr)
+    w2, b2, ws2, bs2 = backward_propagation_layer([r[:] for r in w], b[:], x, err, lr, pr, [r[:] for r in ws], bs[:], xs, err_s)
+    assert len(w2) == AC and len(w2[0]) == FE and all(s in (0, 1) for r in ws2 for s in r)
+    assert isinstance(out_f[0], float) and not math.isnan(dec(out[0], out_s[0]))
+
+
+def test_aggregation_trace_rules():
+    """src/aggregation/prover.rs:63-64,98-154; src/aggregation/air.rs:110-115,135-145."""
+    p = T.aggregation_prover(16, T.options())
+    rows = p.compute_iterative_trace_augmented()
+    assert len(rows) == 32 and len(rows[0]) == 120
+    k = p.k
+    for i in range(31):  # k*(next - cur) - next.update == 0 on every transition
+        for c in range(60):
+            assert (k * (rows[i + 1][c] - rows[i][c]) - rows[i + 1][c + 60]) % P == 0
+    assert rows[17][60:] == [0] * 60 and rows[18] == rows[17] and rows[31] == rows[17]
+    pub = p.get_pub_inputs()
+    assert len(pub.to_elements()) == 123 and pub.steps == 18 and pub.to_elements()[-1] == 18
+    air = p.describe(p.build_trace())
+    assert len(air["assertions"]) == 120 and all(a[1] == 17 for a in air["assertions"])
+
+
+def test_mimc_trace_matches_oracle(oracle):
+    p = T.mimc_prover(3, 128, T.options(blowup=8))
+    assert p.build_trace().to_bytes() == oracle.mimc_trace(p.seeds, 128, p.rc)
+    assert Z.mimc_cipher(5, 10**6, 3) == oracle.mimc_cipher(5, 10**6, 3)
+
+
+def test_invalid_inputs_panic():
+    """tests/integration_tests.rs:201-230."""
+    with pytest.raises(AssertionError):
+        Z.TrainingUpdateProver(T.options(), [[0] * 9] * 6, [0] * 6, [[0] * 9] * 6, [0] * 6, [[0] * 9], [[0] * 9], [[0] * 6], 1, 1, 2)
+    with pytest.raises(ValueError):
+        Z.MimcProver(T.options(), [1], 100)
