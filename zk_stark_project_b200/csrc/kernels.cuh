@@ -41,18 +41,19 @@ __device__ __forceinline__ size_t lde_addr(const LdeMat& m, uint32_t k, uint32_t
 }
 
 // ------------------------------------------------------------------------------------------------
-// transpose: column-major [w][n] -> row-major [n][w]   (first step of K1)
-__global__ void k_transpose_cols(const fe* __restrict__ in, fe* __restrict__ out, uint32_t n, uint32_t w) {
+// transpose: `wc` columns of a column-major matrix (column length n) -> columns [0, wc) of a row-major matrix
+// with row stride `out_stride`   (first step of K1; called per column group)
+__global__ void k_transpose_cols(const fe* __restrict__ in, fe* __restrict__ out, uint32_t n, uint32_t wc, uint32_t out_stride) {
     __shared__ uint4 tile[32][33];
     const uint32_t i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
     for (uint32_t jj = threadIdx.y; jj < 32; jj += blockDim.y) {
         uint32_t j = j0 + jj, i = i0 + threadIdx.x;
-        if (j < w && i < n) tile[jj][threadIdx.x] = reinterpret_cast<const uint4*>(in)[(size_t)j * n + i];
+        if (j < wc && i < n) tile[jj][threadIdx.x] = reinterpret_cast<const uint4*>(in)[(size_t)j * n + i];
     }
     __syncthreads();
     for (uint32_t ii = threadIdx.y; ii < 32; ii += blockDim.y) {
         uint32_t i = i0 + ii, j = j0 + threadIdx.x;
-        if (j < w && i < n) reinterpret_cast<uint4*>(out)[(size_t)i * w + j] = tile[threadIdx.x][ii];
+        if (j < wc && i < n) reinterpret_cast<uint4*>(out)[(size_t)i * out_stride + j] = tile[threadIdx.x][ii];
     }
 }
 

@@ -86,6 +86,8 @@ struct zkb_ctx {
     PowTab roots{}, inv3tab{};
     uint32_t inv3_l1 = 0;
     cudaEvent_t ev[16];
+    cudaEvent_t ev_group[17];          // per column group: "H2D of this group has landed"
+    cudaStream_t copy_stream = nullptr;  // trace ingest overlaps the NTTs of earlier column groups
     bool ev_ok = false;
 
     // ==========================================================================================================
@@ -107,6 +109,8 @@ struct zkb_ctx {
         sm_count = prop.multiProcessorCount;
         CK(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         for (auto& x : ev) CK(cudaEventCreate(&x));
+        for (auto& x : ev_group) CK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+        CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
         ev_ok = true;
         memset(&times, 0, sizeof(times));
     }
@@ -118,7 +122,7 @@ struct zkb_ctx {
             b->release();
         for (auto& b : d_fri_evals) b.release();
         for (auto& b : d_fri_tree) b.release();
-        if (ev_ok) for (auto& x : ev) cudaEventDestroy(x);
+        if (ev_ok) { for (auto& x : ev) cudaEventDestroy(x); for (auto& x : ev_group) cudaEventDestroy(x); cudaStreamDestroy(copy_stream); }
     }
 
     void h2d(void* dst, const void* src, size_t bytes) { CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream)); }
@@ -276,34 +280,59 @@ struct zkb_ctx {
         stage = ST_BEGUN;
     }
 
-    // K1-K4.  src: column-major [w][n] in device memory
-    void trace_commit_device(const fe* d_src, uint8_t root_out[32]) {
+    // K1-K4.  The trace is committed column group by column group (16 columns): [H2D] -> transpose -> inverse NTT ->
+    // coset LDE.  Column groups are independent until the rows are hashed, so the host-to-device copy of group g+1
+    // (copy stream) overlaps the transforms of group g, and a group's polynomials (n*16 elements) stay L2-resident
+    // while all beta cosets are evaluated from them.
+    // Group width: 48 columns when the trace comes from the host (5 groups at w = 240: the first copy exposes < 1 ms, every
+    // launch still fills > 25 waves of resident blocks); one group when the trace is already in HBM (no launch tails).
+    void trace_commit(const uint8_t* const* host_cols, const fe* d_src, uint8_t root_out[32]) {
+        const uint32_t GROUP_W = host_cols ? 48u : air.w;
         if (stage != ST_BEGUN) throw StateError("zkb_trace_commit: call zkb_begin first");
         const uint64_t n = air.n, N = air.lde_size();
         const uint32_t w = air.w;
-        CK(cudaEventRecord(ev[1], stream));
-        // K1: transpose + inverse NTT -> polys row-major [n][w]
+        const uint32_t ngroups = (w + GROUP_W - 1) / GROUP_W;
         d_bufA.ensure(n * w * 16); d_bufB.ensure(n * w * 16);
-        {
-            dim3 grid((unsigned)((n + 31) / 32), (w + 31) / 32), block(32, 8);
-            k_transpose_cols<<<grid, block, 0, stream>>>(d_src, d_bufA.as<fe>(), (uint32_t)n, w);
-            check_launch();
-        }
-        {
-            Xform x{d_bufA.as<fe>(), w, 0, d_bufB.as<fe>(), w, 0, w, log_n, true, false, 0, true, HF::from_u64(n).inv()};
-            run_xform(x, d_tmp1, d_tmp2);
-            d_polys = d_bufB.as<fe>();
-        }
-        CK(cudaEventRecord(ev[2], stream));
-        // K2: coset LDE into the panel layout
         d_lde.ensure(N * w * 16);
-        {
-            Xform x{d_polys, w, 0, d_lde.as<fe>(), w, 0, w, log_n, false, true, log_N, false, HF()};
-            lde_log_p = run_xform(x, d_tmp1, d_tmp2);
+        d_tree.ensure(2 * N * 32);
+        CK(cudaEventRecord(ev[0], stream));
+        if (host_cols) {
+            d_trace.ensure((size_t)w * n * 16);
+            for (uint32_t j = 0; j < w; j++) if (!host_cols[j]) throw InvalidArg("null trace column");
+            // the copy stream must not start before earlier work on the compute stream (previous proof) is done
+            CK(cudaEventRecord(ev_group[16], stream));
+            CK(cudaStreamWaitEvent(copy_stream, ev_group[16], 0));
+            if (ngroups > 16) throw InvalidArg("too many column groups");
+            for (uint32_t g = 0; g < ngroups; g++) {
+                const uint32_t c0 = g * GROUP_W, wc = std::min(GROUP_W, w - c0);
+                bool contiguous = true;
+                for (uint32_t j = 1; j < wc; j++) if (host_cols[c0 + j] != host_cols[c0] + (size_t)j * n * 16) contiguous = false;
+                uint8_t* dst = d_trace.as<uint8_t>() + (size_t)c0 * n * 16;
+                if (contiguous) CK(cudaMemcpyAsync(dst, host_cols[c0], (size_t)wc * n * 16, cudaMemcpyHostToDevice, copy_stream));
+                else for (uint32_t j = 0; j < wc; j++) CK(cudaMemcpyAsync(dst + (size_t)j * n * 16, host_cols[c0 + j], n * 16, cudaMemcpyHostToDevice, copy_stream));
+                CK(cudaEventRecord(ev_group[g], copy_stream));
+            }
+            d_src = d_trace.as<fe>();
+        }
+        d_polys = d_bufB.as<fe>();
+        const HF n_inv = HF::from_u64(n).inv();
+        for (uint32_t g = 0; g < ngroups; g++) {
+            const uint32_t c0 = g * GROUP_W, wc = std::min(GROUP_W, w - c0);
+            if (host_cols) CK(cudaStreamWaitEvent(stream, ev_group[g], 0));
+            {
+                dim3 grid((unsigned)((n + 31) / 32), (wc + 31) / 32), block(32, 8);
+                k_transpose_cols<<<grid, block, 0, stream>>>(d_src + (size_t)c0 * n, d_bufA.as<fe>() + c0, (uint32_t)n, wc, w);
+                check_launch();
+            }
+            // K1: interpolate (inverse NTT, scaled by 1/n) -> polys row-major [n][w]
+            Xform xi{d_bufA.as<fe>(), w, c0, d_bufB.as<fe>(), w, c0, wc, log_n, true, false, 0, true, n_inv};
+            run_xform(xi, d_tmp1, d_tmp2);
+            // K2: coset LDE into the panel layout
+            Xform xl{d_polys, w, c0, d_lde.as<fe>(), w, c0, wc, log_n, false, true, log_N, false, HF()};
+            lde_log_p = run_xform(xl, d_tmp1, d_tmp2);
         }
         CK(cudaEventRecord(ev[3], stream));
         // K3: leaves
-        d_tree.ensure(2 * N * 32);
         k_hash_lde_rows<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(lde_mat(), d_tree.as<uint32_t>() + N * 8);
         check_launch();
         CK(cudaEventRecord(ev[4], stream));
@@ -315,11 +344,17 @@ struct zkb_ctx {
         parts.commitments.push_back(root);
         memcpy(ts.trace_root, root.b, 32);
         if (root_out) memcpy(root_out, root.b, 32);
-        CK(cudaEventElapsedTime(&times.interpolate, ev[1], ev[2]));
-        CK(cudaEventElapsedTime(&times.lde, ev[2], ev[3]));
+        // interpolation and LDE are interleaved per group: report them together under `lde`, `interpolate` = 0
+        times.h2d = 0; times.interpolate = 0;
+        CK(cudaEventElapsedTime(&times.lde, ev[0], ev[3]));
         CK(cudaEventElapsedTime(&times.leaf_hash, ev[3], ev[4]));
         CK(cudaEventElapsedTime(&times.merkle, ev[4], ev[5]));
         stage = ST_TRACE;
+    }
+    void trace_commit_device(const fe* d_src, uint8_t root_out[32]) { trace_commit(nullptr, d_src, root_out); }
+    void trace_commit_host(const uint8_t* const* cols, uint8_t root_out[32]) {
+        if (!cols) throw InvalidArg("null trace columns");
+        trace_commit(cols, nullptr, root_out);
     }
     const fe* upload_cols(const uint8_t* const* cols, uint32_t w, uint64_t n, DevBuf& dst) {
         if (!cols) throw InvalidArg("null trace columns");
@@ -329,13 +364,6 @@ struct zkb_ctx {
         if (contiguous) h2d(dst.p, cols[0], (size_t)w * n * 16);
         else for (uint32_t j = 0; j < w; j++) h2d((uint8_t*)dst.p + (size_t)j * n * 16, cols[j], n * 16);
         return dst.as<fe>();
-    }
-    void trace_commit_host(const uint8_t* const* cols, uint8_t root_out[32]) {
-        if (stage != ST_BEGUN) throw StateError("zkb_trace_commit: call zkb_begin first");
-        CK(cudaEventRecord(ev[0], stream));
-        const fe* d = upload_cols(cols, air.w, air.n, d_trace);
-        trace_commit_device(d, root_out);
-        CK(cudaEventElapsedTime(&times.h2d, ev[0], ev[1]));
     }
 
     // K5
