@@ -143,6 +143,19 @@ int32_t zkb_grind(zkb_ctx* ctx, const uint8_t seed[32], uint32_t bits, uint64_t*
 int32_t zkb_query(zkb_ctx* ctx, uint32_t which, const uint32_t* positions, uint32_t n_pos, uint8_t* rows_out,
                   uint8_t** proof_out, uint64_t* proof_len);
 
+/* ---- one large proof sharded across the GPUs of a node (BASELINE.json configs[4]) -------------------------
+ * One process per GPU.  Rank r owns trace columns [r*w/G, (r+1)*w/G): ingest, interpolation and the coset LDE are column-
+ * local; an NCCL all-to-all over NVLink turns column shards into row shards for leaf hashing and the Merkle subtrees, whose
+ * roots are all-gathered; constraint evaluation, OOD and DEEP are column-local partial sums combined by an all-gather.
+ * `air` describes the WHOLE trace (global width, all assertions); `local_cols` holds this rank's w/G columns.
+ * Every rank returns the same proof bytes.  G and w/G must be powers of two; the aggregation AIR is not shardable. */
+int32_t zkb_mg_unique_id(uint8_t out[128]);                                         /* ncclGetUniqueId, on rank 0 */
+int32_t zkb_mg_init(zkb_ctx* ctx, int32_t rank, int32_t world, const uint8_t id[128]); /* ncclCommInitRank (collective) */
+int32_t zkb_mg_prove(zkb_ctx* ctx, const zkb_air_desc* air, const uint8_t* const* local_cols, uint64_t force_nonce,
+                     uint8_t** proof_out, uint64_t* proof_len, zkb_transcript* transcript);
+int32_t zkb_mg_prove_device(zkb_ctx* ctx, const zkb_air_desc* air, const void* d_local_trace_colmajor, uint64_t force_nonce,
+                            uint8_t** proof_out, uint64_t* proof_len, zkb_transcript* transcript);
+
 /* ---- helpers next to the path ---------------------------------------------------------- */
 /* device-side MiMC chain trace; out_cols_colmajor: w*n elements, host memory */
 int32_t zkb_mimc_trace(zkb_ctx* ctx, const uint8_t* seeds, uint32_t w, uint64_t n, const uint8_t* round_constants,

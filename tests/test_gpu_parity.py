@@ -196,3 +196,18 @@ def test_staged_api_matches_one_shot(gpu_ctx, oracle):
     rem, cnt = C.create_string_buffer(16 * 64), C.c_uint64()
     gpu_ctx.check(lib.zkb_fri_remainder(h, rem, C.byref(cnt), root))
     assert root.raw == bytes(ts.remainder_commitment)
+
+
+def test_column_sharded_proof_two_gpus():
+    """SURVEY §8e / BASELINE configs[4]: a proof produced cooperatively by 2 GPUs (column-sharded LDE, NVLink all-to-all,
+    row-sharded hashing, all-gather of subtree roots) is byte-identical to the single-GPU proof."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    cases = '[["mimc", 64, 1024, 8], ["mimc", 16, 256, 8], ["training", 128, 512, 16]]'
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29611", "tests/mg_worker.py", cases], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "mg ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

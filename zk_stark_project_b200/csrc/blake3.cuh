@@ -95,7 +95,9 @@ __host__ __device__ __forceinline__ void b3_parent(const uint32_t l[8], const ui
 // BLAKE3 of `count` field elements (16 B each) read from base[j * stride]; this is
 // Blake3_256::hash_elements over a matrix row stored with an arbitrary element stride.
 // count <= 255 (TraceInfo width limit) => at most 4 chunks, handled with a two-slot CV stack.
-__device__ __forceinline__ void b3_hash_elems(const fe* __restrict__ base, size_t stride, uint32_t count, uint32_t out[8]) {
+// Element e lives at base[(e >> log_blk) * blk_stride + (e & (2^log_blk - 1)) * stride] (log_blk = 31: one block).
+__device__ __forceinline__ void b3_hash_elems(const fe* __restrict__ base, size_t stride, uint32_t count, uint32_t out[8],
+                                              uint32_t log_blk, size_t blk_stride) {
     const uint32_t nchunks = count <= 64 ? 1u : (count + 63u) / 64u;
     uint32_t st0[8], st1[8];
     for (uint32_t c = 0; c < nchunks; c++) {
@@ -111,7 +113,10 @@ __device__ __forceinline__ void b3_hash_elems(const fe* __restrict__ base, size_
 #pragma unroll
             for (uint32_t q = 0; q < 4; q++) {
                 uint4 v = make_uint4(0, 0, 0, 0);
-                if (q < nb) v = *reinterpret_cast<const uint4*>(base + (size_t)(eb + q) * stride);
+                if (q < nb) {
+                    const uint32_t e = eb + q;
+                    v = *reinterpret_cast<const uint4*>(base + (size_t)(e >> log_blk) * blk_stride + (size_t)(e & ((1u << log_blk) - 1u)) * stride);
+                }
                 m[4 * q] = v.x; m[4 * q + 1] = v.y; m[4 * q + 2] = v.z; m[4 * q + 3] = v.w;
             }
             uint32_t flags = (b == 0 ? B3_CHUNK_START : 0u);

@@ -29,15 +29,32 @@ __device__ __forceinline__ fe powtab(const PowTab& t, uint32_t e) {
     return fe_mul(a, b);
 }
 
+// LDE matrix descriptor.  Single GPU: log_shard = 0, bw = w, log_bw = 31 and the layout is the panel layout above.
+// Column-sharded multi-GPU proofs (G = 2^log_shard ranks) store the array as [G][panels][bw][P'] with P' = P/G = 2^log_p:
+//   send view (view = 0) on rank r: its bw = w/G columns, all rows; chunk index = slot div P' (the destination rank)
+//   recv view (view = 1) on rank q: all w columns, its rows (slots [q P', (q+1) P')); chunk index = column div bw (the source)
+// The NVLink all-to-all exchanges chunk q of rank r with chunk r of rank q, so both views share one address formula.
 struct LdeMat {
     fe* data;
-    uint32_t log_n, log_beta, w, log_p;
+    uint32_t log_n, log_beta, w, log_p;   // log_p: slots per stored chunk (P' = P >> log_shard)
+    uint32_t log_shard, bw, log_bw, view, q_self;
+    uint64_t blk_stride;                  // elements between column blocks (recv view): panels * bw * P'
 };
-__device__ __forceinline__ size_t lde_addr(const LdeMat& m, uint32_t k, uint32_t i, uint32_t j) {
-    const uint32_t lt = m.log_n - m.log_p;
+__device__ __forceinline__ uint32_t lde_full_log_p(const LdeMat& m) { return m.log_p + m.log_shard; }
+// address of (row (k, i), column 0 of block 0)
+__device__ __forceinline__ size_t lde_row_base(const LdeMat& m, uint32_t k, uint32_t i) {
+    const uint32_t lt = m.log_n - lde_full_log_p(m);
     const uint32_t t_low = i & ((1u << lt) - 1u), slot = i >> lt;
     const size_t panel = ((size_t)k << lt) + t_low;
-    return ((panel * m.w + j) << m.log_p) + slot;
+    const size_t np = (size_t)1 << (m.log_beta + lt);
+    const uint32_t chunk = m.view == 0 ? (slot >> m.log_p) : 0u;
+    return (((size_t)chunk * np + panel) * m.bw << m.log_p) + (slot & ((1u << m.log_p) - 1u));
+}
+__device__ __forceinline__ size_t lde_col_off(const LdeMat& m, uint32_t j) {
+    return (size_t)(j >> m.log_bw) * m.blk_stride + ((size_t)(j & ((1u << m.log_bw) - 1u)) << m.log_p);
+}
+__device__ __forceinline__ size_t lde_addr(const LdeMat& m, uint32_t k, uint32_t i, uint32_t j) {
+    return lde_row_base(m, k, i) + lde_col_off(m, j);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -82,6 +99,7 @@ struct NttPass {
     uint32_t log_tab;              // root table covers <w_{2^log_tab}>
     uint32_t log_lde;              // log2(n * beta) for coset transforms
     uint32_t out_panel;            // final pass of an LDE: write the panel layout
+    uint32_t log_shard;            // panel layout split into 2^log_shard slot chunks (multi-GPU send view)
     uint32_t do_scale;             // multiply outputs by `scale` (1/n for interpolation)
     fe scale;
     PowTab roots;                  // w_{2^log_tab}^e
@@ -193,10 +211,15 @@ __global__ void __launch_bounds__(256, 3) k_ntt_pass(const NttPass p) {
     if (p.out_panel) {
         // panel = k*2^a + t_low, slot = t_high; consecutive threads write consecutive slots of one column
         const size_t panel = ((size_t)k << p.a) + t_low;
-        fe* dst = p.out + ((panel * p.w_out + p.col0_out + c_base) << logS);
+        const uint32_t lp = logS - p.log_shard;                       // slots per stored chunk
+        const size_t np = (size_t)1 << (p.log_lde - p.log_n + p.a);   // panels = beta * 2^a
         for (uint32_t idx = threadIdx.x; idx < E; idx += blockDim.x) {
             const uint32_t jj = idx >> logS, th = idx & (S - 1u);
-            if (c_base + jj < p.ncols) fe_store(dst + ((size_t)jj << logS) + th, sm[th * rs + jj]);
+            if (c_base + jj < p.ncols) {
+                const size_t chunk = th >> lp;
+                fe_store(p.out + (((chunk * np + panel) * p.w_out + p.col0_out + c_base + jj) << lp) + (th & ((1u << lp) - 1u)),
+                         sm[th * rs + jj]);
+            }
         }
     } else {
         fe* dst = out + (((size_t)u0 << p.b) + t_low) * p.w_out + p.col0_out + c_base;
@@ -222,20 +245,24 @@ __global__ void k_scale_pow(fe* x, uint64_t n, PowTab base, fe scale) {
 
 // ------------------------------------------------------------------------------------------------
 // K3: leaf = Blake3_256::hash_elements(LDE row)  (RowMatrix::commit_to_rows; src/training/prover.rs:225,280)
-// one thread per LDE row, enumerated (panel, slot) so that a warp reads 32 consecutive slots per column
-__global__ void __launch_bounds__(128) k_hash_lde_rows(const LdeMat m, uint32_t* __restrict__ leaves) {
+// one thread per stored LDE row, enumerated (panel, slot) so that a warp reads 32 consecutive slots per column.
+// leaves: digest array indexed by (global leaf index - leaf0); in the multi-GPU recv view a rank stores and hashes only
+// the rows of its slot chunk, which are the contiguous leaves [q N/G, (q+1) N/G).
+__global__ void __launch_bounds__(128) k_hash_lde_rows(const LdeMat m, uint32_t* __restrict__ leaves, uint64_t leaf0) {
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t log_N = m.log_n + m.log_beta;
-    if (gid >> log_N) return;
-    const uint32_t lt = m.log_n - m.log_p;
-    const uint32_t slot = (uint32_t)gid & ((1u << m.log_p) - 1u);
-    const uint32_t panel = (uint32_t)(gid >> m.log_p);
+    const uint32_t lpf = lde_full_log_p(m), lt = m.log_n - lpf;
+    const uint32_t log_rows = m.log_beta + lt + (m.view == 0 ? lpf : m.log_p);   // rows stored on this rank
+    if (gid >> log_rows) return;
+    const uint32_t lslots = m.view == 0 ? lpf : m.log_p;
+    const uint32_t s = (uint32_t)gid & ((1u << lslots) - 1u);
+    const uint32_t panel = (uint32_t)(gid >> lslots);
+    const uint32_t slot = m.view == 0 ? s : ((m.q_self << m.log_p) + s);
     const uint32_t k = panel >> lt, t_low = panel & ((1u << lt) - 1u);
     const uint32_t i = t_low + (slot << lt);
     const uint64_t r = ((uint64_t)i << m.log_beta) + k;
     uint32_t d[8];
-    b3_hash_elems(m.data + (((size_t)panel * m.w) << m.log_p) + slot, (size_t)1 << m.log_p, m.w, d);
-    uint4* o = reinterpret_cast<uint4*>(leaves + r * 8);
+    b3_hash_elems(m.data + lde_row_base(m, k, i), (size_t)1 << m.log_p, m.w, d, m.log_bw, m.blk_stride);
+    uint4* o = reinterpret_cast<uint4*>(leaves + (r - leaf0) * 8);
     o[0] = make_uint4(d[0], d[1], d[2], d[3]);
     o[1] = make_uint4(d[4], d[5], d[6], d[7]);
 }
@@ -245,7 +272,7 @@ __global__ void __launch_bounds__(128) k_hash_strided_rows(const fe* __restrict_
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
     uint32_t d[8];
-    b3_hash_elems(e + i, rows, count, d);
+    b3_hash_elems(e + i, rows, count, d, 31, 0);
     uint4* o = reinterpret_cast<uint4*>(leaves + i * 8);
     o[0] = make_uint4(d[0], d[1], d[2], d[3]);
     o[1] = make_uint4(d[4], d[5], d[6], d[7]);
@@ -296,9 +323,9 @@ __global__ void __launch_bounds__(128) k_eval_constraints(const EvalParams p) {
     const LdeMat& m = p.lde;
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >> (m.log_n + p.log_ce)) return;
-    const uint32_t lt = m.log_n - m.log_p;
-    const uint32_t slot = (uint32_t)gid & ((1u << m.log_p) - 1u);
-    const uint32_t t_low = (uint32_t)(gid >> m.log_p) & ((1u << lt) - 1u);
+    const uint32_t lpf = lde_full_log_p(m), lt = m.log_n - lpf;
+    const uint32_t slot = (uint32_t)gid & ((1u << lpf) - 1u);
+    const uint32_t t_low = (uint32_t)(gid >> lpf) & ((1u << lt) - 1u);
     const uint32_t kc = (uint32_t)(gid >> m.log_n);
     const uint32_t k = kc << (m.log_beta - p.log_ce);
     const uint32_t i = t_low + (slot << lt);
@@ -306,8 +333,8 @@ __global__ void __launch_bounds__(128) k_eval_constraints(const EvalParams p) {
     const uint32_t ci = (i << p.log_ce) + kc;
     const uint32_t log_N = m.log_n + m.log_beta;
     const uint32_t r = (i << m.log_beta) + k;
-    const fe* cur = m.data + lde_addr(m, k, i, 0);
-    const fe* nxt = m.data + lde_addr(m, k, i1, 0);
+    const fe* cur = m.data + lde_row_base(m, k, i);   // send view / single GPU: columns are local, stride 2^log_p
+    const fe* nxt = m.data + lde_row_base(m, k, i1);
     const size_t cs = (size_t)1 << m.log_p;  // column stride
 
     // x = 3 * w_N^r
@@ -561,6 +588,24 @@ __global__ void k_gather_digests(const uint32_t* __restrict__ digests, const uin
 }
 
 // ------------------------------------------------------------------------------------------------
+// multi-GPU: out[i] = sum_g parts[g * stride + i]  (field sum of per-rank partial vectors after an all-gather;
+// NCCL has no mod-p reduction for 128-bit elements)
+__global__ void k_sum_partials(const fe* __restrict__ parts, uint32_t g, uint64_t stride, uint64_t n, fe* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe s = fe_load(parts + i);
+    for (uint32_t q = 1; q < g; q++) s = fe_add(s, fe_load(parts + (uint64_t)q * stride + i));
+    fe_store(out + i, s);
+}
+// multi-GPU DEEP: ab[m][1] += sum_i gamma'_i H_i[m]   (ab[m][0] = ab[m][1] = A[m] on entry)
+__global__ void k_deep_add_h(fe* __restrict__ ab, uint32_t n, const fe* __restrict__ hcoef, uint32_t c, const fe* __restrict__ gamma_h) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    fe b = fe_zero();
+    for (uint32_t i = 0; i < c; i++) b = fe_add(b, fe_mul(fe_load(hcoef + (size_t)i * n + m), fe_ldg(gamma_h + i)));
+    fe_store(ab + (size_t)m * 2 + 1, fe_add(fe_load(ab + (size_t)m * 2 + 1), b));
+}
+
 // device-side MiMC chain trace: col_j[0] = seed_j, col_j[i+1] = (col_j[i] + rc[i mod L])^7
 // round function from src/helper.rs:213-220, constants from :404-406; output column-major [w][n]
 __global__ void k_mimc_trace(const fe* __restrict__ seeds, uint32_t w, uint64_t n, const fe* __restrict__ rc, uint32_t L, fe* __restrict__ out) {
@@ -587,7 +632,7 @@ __global__ void k_test_hash(const fe* data, uint32_t count, uint32_t nrows, uint
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nrows) return;
     uint32_t d[8];
-    b3_hash_elems(data + (size_t)i * count, 1, count, d);
+    b3_hash_elems(data + (size_t)i * count, 1, count, d, 31, 0);
     for (int q = 0; q < 8; q++) out[i * 8 + q] = d[q];
 }
 

@@ -7,6 +7,8 @@
 // src/training/prover.rs:221-301 and src/aggregation/prover.rs:194-249) with every stage on the GPU.
 // There is no CPU fallback: without a CUDA device every entry point fails.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
@@ -41,6 +43,42 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
+
+// NCCL is resolved lazily (dlopen) so the single-GPU path never depends on it; if the process already loaded an NCCL
+// with the same SONAME (e.g. torch's), that copy is reused.
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    void load() {
+        if (h) return;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) { h = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+        if (!h) throw CudaError(std::string("cannot load NCCL: ") + dlerror());
+        auto sym = [&](const char* n) { void* f = dlsym(h, n); if (!f) throw CudaError(std::string("NCCL symbol missing: ") + n); return f; };
+        GetUniqueId = (decltype(GetUniqueId))sym("ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))sym("ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))sym("ncclCommDestroy");
+        GroupStart = (decltype(GroupStart))sym("ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))sym("ncclGroupEnd");
+        Send = (decltype(Send))sym("ncclSend");
+        Recv = (decltype(Recv))sym("ncclRecv");
+        AllGather = (decltype(AllGather))sym("ncclAllGather");
+        GetErrorString = (decltype(GetErrorString))sym("ncclGetErrorString");
+    }
+};
+static NcclApi g_nccl;
+#define NK(call)                                                                                                        \
+    do {                                                                                                                \
+        ncclResult_t r_ = (call);                                                                                       \
+        if (r_ != ncclSuccess) throw CudaError(std::string(#call) + " failed: " + g_nccl.GetErrorString(r_));           \
+    } while (0)
 
 static inline fe to_fe(const HF& h) {
     fe r;
@@ -90,11 +128,30 @@ struct zkb_ctx {
     cudaStream_t copy_stream = nullptr;  // trace ingest overlaps the NTTs of earlier column groups
     bool ev_ok = false;
 
+    // ---- multi-GPU (column-sharded single proof) -----------------------------------------------------------------
+    ncclComm_t comm = nullptr;
+    int mg_rank = 0, mg_world = 1;
+    uint32_t log_g = 0;
+    bool mg_active = false;             // the proof in flight is sharded
+    DevBuf d_lde_rows, d_mg_a, d_mg_b;  // recv view of the LDE; all-gather staging
+    std::vector<Digest32> mg_cap;       // heap of the replicated top log G levels: cap[1] = root, cap[G + q] = subtree root q
+
     // ==========================================================================================================
     void count() { launches++; }
-    LdeMat lde_mat() const { return LdeMat{d_lde.as<fe>(), log_n, log_beta, air.w, lde_log_p}; }
-    LdeMat comp_mat() const { return LdeMat{d_comp_lde.as<fe>(), log_n, log_beta, c, comp_log_p}; }
-    LdeMat ab_mat() const { return LdeMat{d_ab_lde.as<fe>(), log_n, log_beta, 2, ab_log_p}; }
+    LdeMat std_mat(fe* data, uint32_t w, uint32_t log_p) const { return LdeMat{data, log_n, log_beta, w, log_p, 0, w, 31, 0, 0, 0}; }
+    // single GPU: the whole trace LDE; multi-GPU: the send view (this rank's columns, all rows)
+    LdeMat lde_mat() const {
+        if (!mg_active) return std_mat(d_lde.as<fe>(), air.w, lde_log_p);
+        return LdeMat{d_lde.as<fe>(), log_n, log_beta, air.w >> log_g, lde_log_p - log_g, log_g, air.w >> log_g, 31, 0, (uint32_t)mg_rank, 0};
+    }
+    // multi-GPU recv view: all columns, this rank's rows
+    LdeMat lde_rows_mat() const {
+        const uint32_t wl = air.w >> log_g, lp = lde_log_p - log_g;
+        const uint64_t np = (uint64_t)1 << (log_beta + log_n - lde_log_p);
+        return LdeMat{d_lde_rows.as<fe>(), log_n, log_beta, air.w, lp, log_g, wl, log2u(wl), 1, (uint32_t)mg_rank, (np * wl) << lp};
+    }
+    LdeMat comp_mat() const { return std_mat(d_comp_lde.as<fe>(), c, comp_log_p); }
+    LdeMat ab_mat() const { return std_mat(d_ab_lde.as<fe>(), 2, ab_log_p); }
 
     void init(int dev, void* strm) {
         int ndev = 0;
@@ -118,8 +175,10 @@ struct zkb_ctx {
         cudaSetDevice(device);
         cudaStreamSynchronize(stream);
         for (DevBuf* b : {&d_trace, &d_bufA, &d_bufB, &d_tmp1, &d_tmp2, &d_lde, &d_tree, &d_small, &d_comp_evals, &d_comp_lde, &d_comp_tree,
-                          &d_ab, &d_ab_lde, &d_deep, &d_roots_lo, &d_roots_hi, &d_inv3_lo, &d_inv3_hi, &d_pow3, &d_aux, &d_gather, &d_user_trace})
+                          &d_ab, &d_ab_lde, &d_deep, &d_roots_lo, &d_roots_hi, &d_inv3_lo, &d_inv3_hi, &d_pow3, &d_aux, &d_gather, &d_user_trace,
+                          &d_lde_rows, &d_mg_a, &d_mg_b})
             b->release();
+        if (comm) { g_nccl.CommDestroy(comm); comm = nullptr; }
         for (auto& b : d_fri_evals) b.release();
         for (auto& b : d_fri_tree) b.release();
         if (ev_ok) { for (auto& x : ev) cudaEventDestroy(x); for (auto& x : ev_group) cudaEventDestroy(x); cudaStreamDestroy(copy_stream); }
@@ -199,6 +258,7 @@ struct zkb_ctx {
         bool inverse, coset_lde;
         uint32_t log_lde;  // coset LDE only
         bool scale; HF scale_by;
+        uint32_t log_shard = 0;  // coset LDE only: split every panel into 2^log_shard slot chunks (multi-GPU send view)
     };
     // returns log_p of the panel layout for LDEs (size of the last pass)
     uint32_t run_xform(const Xform& x, DevBuf& s1, DevBuf& s2) {
@@ -232,6 +292,8 @@ struct zkb_ctx {
                 if (last) {
                     p.out = x.out; p.w_out = x.w_out; p.col0_out = x.col0_out;
                     p.out_panel = x.coset_lde ? 1 : 0;
+                    p.log_shard = x.coset_lde ? x.log_shard : 0;
+                    if (p.log_shard > p.b - p.a) throw InvalidArg("trace too short to shard its LDE panels across this many GPUs");
                     p.out_coset_stride = 0;
                     p.do_scale = x.scale ? 1 : 0; p.scale = to_fe(x.scale_by);
                 } else {
@@ -277,6 +339,7 @@ struct zkb_ctx {
         if (fri_layers > 16) throw InvalidArg("too many FRI layers");
         fri_layer = 0; fri_committed = false;
         positions.clear();
+        mg_active = false;
         stage = ST_BEGUN;
     }
 
@@ -333,7 +396,7 @@ struct zkb_ctx {
         }
         CK(cudaEventRecord(ev[3], stream));
         // K3: leaves
-        k_hash_lde_rows<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(lde_mat(), d_tree.as<uint32_t>() + N * 8);
+        k_hash_lde_rows<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(lde_mat(), d_tree.as<uint32_t>() + N * 8, 0);
         check_launch();
         CK(cudaEventRecord(ev[4], stream));
         // K4: tree
@@ -366,32 +429,167 @@ struct zkb_ctx {
         return dst.as<fe>();
     }
 
-    // K5
-    void constraints_eval(const HF& alpha, uint8_t* evals_out) {
-        if (stage != ST_TRACE) throw StateError("zkb_constraints_eval: trace is not committed");
+    // ---- column-sharded single proof (BASELINE.json configs[4]) ---------------------------------------
+    // Rank r owns columns [r w/G, (r+1) w/G): ingest, interpolation and the coset LDE are column-local.  The LDE's last
+    // pass writes the sharded panel layout [G][panels][w/G][P/G]; one NCCL all-to-all over NVLink (chunk q of rank r <->
+    // chunk r of rank q) turns it into the recv view "all columns x my rows", rows [q N/G, (q+1) N/G) being contiguous
+    // Merkle leaves.  Every rank hashes its rows and builds its subtree; an all-gather of the G subtree roots lets every
+    // rank finish the top log G levels redundantly.
+    void mg_init(int rank, int world, const uint8_t* id_bytes) {
+        if (world < 1 || !is_pow2((uint64_t)world) || rank < 0 || rank >= world) throw InvalidArg("multi-GPU world size must be a power of two");
+        g_nccl.load();
+        CK(cudaSetDevice(device));
+        if (comm) { g_nccl.CommDestroy(comm); comm = nullptr; }
+        ncclUniqueId id;
+        static_assert(sizeof(ncclUniqueId) == 128, "unexpected ncclUniqueId size");
+        memcpy(&id, id_bytes, sizeof(id));
+        NK(g_nccl.CommInitRank(&comm, world, id, rank));
+        mg_rank = rank; mg_world = world; log_g = log2u((uint64_t)world);
+    }
+    void trace_commit_mg(const uint8_t* const* host_cols_local, const fe* d_src, uint8_t root_out[32]) {
+        if (stage != ST_BEGUN) throw StateError("zkb_mg_prove: call zkb_begin first");
+        if (!comm) throw StateError("zkb_mg_init has not been called on this context");
+        const uint64_t n = air.n, N = air.lde_size();
+        const uint32_t w = air.w, G = (uint32_t)mg_world;
+        if (w % G) throw InvalidArg("trace width must be divisible by the number of GPUs");
+        const uint32_t wl = w / G;
+        if (!is_pow2(wl)) throw InvalidArg("columns per GPU must be a power of two");
+        if (air.id == ZKB_AIR_ID_AGGREGATION) throw InvalidArg("the aggregation AIR cannot be column-sharded (replicas only)");
+        if (N / G < 2) throw InvalidArg("LDE domain too small to shard");
+        mg_active = true;
         CK(cudaEventRecord(ev[0], stream));
+        if (host_cols_local) d_src = upload_cols(host_cols_local, wl, n, d_trace);
+        d_bufA.ensure(n * wl * 16); d_bufB.ensure(n * wl * 16);
+        {
+            dim3 grid((unsigned)((n + 31) / 32), (wl + 31) / 32), block(32, 8);
+            k_transpose_cols<<<grid, block, 0, stream>>>(d_src, d_bufA.as<fe>(), (uint32_t)n, wl, wl);
+            check_launch();
+        }
+        Xform xi{d_bufA.as<fe>(), wl, 0, d_bufB.as<fe>(), wl, 0, wl, log_n, true, false, 0, true, HF::from_u64(n).inv()};
+        run_xform(xi, d_tmp1, d_tmp2);
+        d_polys = d_bufB.as<fe>();
+        d_lde.ensure(N * wl * 16);
+        Xform xl{d_polys, wl, 0, d_lde.as<fe>(), wl, 0, wl, log_n, false, true, log_N, false, HF()};
+        xl.log_shard = log_g;
+        lde_log_p = run_xform(xl, d_tmp1, d_tmp2);
+        CK(cudaEventRecord(ev[3], stream));
+        // NVLink transpose: column shards -> row shards
+        d_lde_rows.ensure(N * wl * 16);
+        const size_t chunk = (size_t)(N / G) * wl * 16;  // bytes
+        NK(g_nccl.GroupStart());
+        for (uint32_t q = 0; q < G; q++) {
+            NK(g_nccl.Send(d_lde.as<uint8_t>() + q * chunk, chunk, ncclUint8, (int)q, comm, stream));
+            NK(g_nccl.Recv(d_lde_rows.as<uint8_t>() + q * chunk, chunk, ncclUint8, (int)q, comm, stream));
+        }
+        NK(g_nccl.GroupEnd());
+        CK(cudaEventRecord(ev[6], stream));
+        // K3/K4 on this rank's rows
+        const uint64_t Nl = N / G;
+        d_tree.ensure(2 * Nl * 32);
+        k_hash_lde_rows<<<(unsigned)((Nl + 127) / 128), 128, 0, stream>>>(lde_rows_mat(), d_tree.as<uint32_t>() + Nl * 8, (uint64_t)mg_rank * Nl);
+        check_launch();
+        CK(cudaEventRecord(ev[4], stream));
+        build_merkle(d_tree.as<uint32_t>(), Nl);
+        // all-gather of the subtree roots; the cap is finished on the host by every rank
+        d_gather.ensure(4096 + (size_t)G * 32);
+        NK(g_nccl.AllGather(d_tree.as<uint8_t>() + 32, d_gather.as<uint8_t>(), 32, ncclUint8, comm, stream));
+        CK(cudaEventRecord(ev[5], stream));
+        mg_cap.assign(2 * (size_t)G, Digest32{});
+        d2h(mg_cap.data() + G, d_gather.p, (size_t)G * 32);
+        for (uint32_t i = G - 1; i >= 1; i--) { uint8_t buf[64]; memcpy(buf, mg_cap[2 * i].b, 32); memcpy(buf + 32, mg_cap[2 * i + 1].b, 32); b3_hash_host(buf, 64, mg_cap[i].b); }
+        const Digest32 root = mg_cap[1];
+        parts.commitments.push_back(root);
+        memcpy(ts.trace_root, root.b, 32);
+        if (root_out) memcpy(root_out, root.b, 32);
+        times.h2d = 0;
+        CK(cudaEventElapsedTime(&times.lde, ev[0], ev[3]));
+        CK(cudaEventElapsedTime(&times.interpolate, ev[3], ev[6]));  // reused slot: NVLink all-to-all time
+        CK(cudaEventElapsedTime(&times.leaf_hash, ev[6], ev[4]));
+        CK(cudaEventElapsedTime(&times.merkle, ev[4], ev[5]));
+        stage = ST_TRACE;
+    }
+    // TraceLde::query for a sharded trace: every rank gathers the queried rows / authentication nodes it owns, the
+    // contributions are all-gathered and the owner's copy of each entry is kept.
+    void query_trace_mg(const std::vector<uint32_t>& pos, std::vector<uint8_t>& rows, std::vector<uint8_t>& paths) {
+        const uint32_t np = (uint32_t)pos.size(), w = air.w, G = (uint32_t)mg_world;
+        const uint64_t N = air.lde_size(), Nl = N / G;
+        for (uint32_t p : pos) if (p >= N) throw InvalidArg("query position out of range");
+        std::vector<std::vector<uint64_t>> plan = plan_batch_proof(log_N, pos);
+        std::vector<uint64_t> flat;
+        for (auto& v : plan) flat.insert(flat.end(), v.begin(), v.end());
+        // owner and local heap index of every authentication node
+        std::vector<int> owner(flat.size());
+        std::vector<uint64_t> local(flat.size(), 0);
+        for (size_t t = 0; t < flat.size(); t++) {
+            const uint64_t h = flat[t];
+            const uint32_t d = 63 - (uint32_t)__builtin_clzll(h);
+            if (d <= log_g) { owner[t] = -1; continue; }  // replicated cap
+            const uint64_t off = h - ((uint64_t)1 << d);
+            owner[t] = (int)(off >> (d - log_g));
+            if (owner[t] == mg_rank) local[t] = ((uint64_t)1 << (d - log_g)) + (off & (((uint64_t)1 << (d - log_g)) - 1));
+        }
+        const size_t row_bytes = (size_t)np * w * 16, dig_bytes = flat.size() * 32, mine = ((row_bytes + dig_bytes + 15) / 16) * 16;
+        size_t o_pos = 0, o_idx = 1024, o_out = o_idx + ((flat.size() * 8 + 15) / 16) * 16 + 16, total = o_out + mine;
+        d_gather.ensure(total);
+        d_mg_b.ensure(mine * G);
+        uint8_t* base = d_gather.as<uint8_t>();
+        h2d(base + o_pos, pos.data(), np * 4);
+        if (!flat.empty()) h2d(base + o_idx, local.data(), flat.size() * 8);
+        k_gather_lde_rows<<<(np * w + 127) / 128, 128, 0, stream>>>(lde_rows_mat(), (const uint32_t*)(base + o_pos), np, (fe*)(base + o_out));
+        check_launch();
+        if (!flat.empty()) {
+            k_gather_digests<<<(unsigned)((flat.size() * 2 + 127) / 128), 128, 0, stream>>>(d_tree.as<uint32_t>(), (const uint64_t*)(base + o_idx),
+                                                                                        (uint32_t)flat.size(), (uint32_t*)(base + o_out + row_bytes));
+            check_launch();
+        }
+        NK(g_nccl.AllGather(base + o_out, d_mg_b.p, mine, ncclUint8, comm, stream));
+        std::vector<uint8_t> all(mine * G);
+        d2h(all.data(), d_mg_b.p, all.size());
+        rows.resize(row_bytes);
+        for (uint32_t q = 0; q < np; q++) {
+            const size_t own = pos[q] / Nl;
+            memcpy(&rows[(size_t)q * w * 16], &all[own * mine + (size_t)q * w * 16], (size_t)w * 16);
+        }
+        std::vector<uint8_t> dig(dig_bytes);
+        for (size_t t = 0; t < flat.size(); t++) {
+            if (owner[t] < 0) memcpy(&dig[t * 32], mg_cap[flat[t]].b, 32);
+            else memcpy(&dig[t * 32], &all[(size_t)owner[t] * mine + row_bytes + t * 32], 32);
+        }
+        paths = batch_proof_bytes(log_N, plan, dig.data());
+    }
+
+    // K5.  The evaluator works on a window of `ncols` trace columns starting at global column `col0` (the whole trace on
+    // one GPU; this rank's columns in a column-sharded proof).  Every term of the combined evaluation is linear in
+    // per-column sums, so per-rank partial results add up to the full composition trace.
+    void constraints_eval_window(const HF& alpha, const LdeMat& mat, uint32_t col0, uint32_t ncols, fe* out) {
         const uint32_t nt = air.num_transition(), na = (uint32_t)air.assertions.size();
         const uint64_t n = air.n, ce = (uint64_t)1 << log_ce;
         // ConstraintCompositionCoefficients::draw_algebraic: alpha^0.. for transition, continuing for boundary  [A.5]
-        std::vector<HF> tcoef(nt), acoef(na), aval(na);
-        std::vector<uint32_t> acol(na);
-        { HF cur = HF::raw(1); for (auto& x : tcoef) { x = cur; cur = cur * alpha; } for (auto& x : acoef) { x = cur; cur = cur * alpha; } }
+        std::vector<HF> tcoef(nt), acoef_all(na);
+        { HF cur = HF::raw(1); for (auto& x : tcoef) { x = cur; cur = cur * alpha; } for (auto& x : acoef_all) { x = cur; cur = cur * alpha; } }
+        const bool windowed = !(col0 == 0 && ncols == air.w);
+        if (windowed && air.id == ZKB_AIR_ID_AGGREGATION) throw InvalidArg("the aggregation AIR couples columns i and i+d and cannot be column-sharded");
         EvalParams p{};
-        p.lde = lde_mat(); p.air_id = air.id; p.log_ce = log_ce; p.n_trans = nt;
+        p.lde = mat; p.air_id = air.id; p.log_ce = log_ce;
+        p.n_trans = windowed ? ncols : nt;
         const HF g = HF::root_of_unity(log_n);
+        std::vector<HF> acoef, aval;
+        std::vector<uint32_t> acol;
         uint32_t ng = 0;
         for (uint32_t i = 0; i < na; i++) {
             if (i == 0 || air.assertions[i].step != air.assertions[i - 1].step) {
-                p.g_off[ng] = i; p.g_point[ng] = to_fe(g.pow(air.assertions[i].step)); ng++;
+                p.g_off[ng] = (uint32_t)acol.size(); p.g_point[ng] = to_fe(g.pow(air.assertions[i].step)); ng++;
             }
-            acol[i] = air.assertions[i].col; aval[i] = air.assertions[i].value;
+            const uint32_t col = air.assertions[i].col;
+            if (col >= col0 && col < col0 + ncols) { acol.push_back(col - col0); aval.push_back(air.assertions[i].value); acoef.push_back(acoef_all[i]); }
         }
-        p.g_off[ng] = na; p.n_groups = ng;
+        const uint32_t nl = (uint32_t)acol.size();
+        p.g_off[ng] = nl; p.n_groups = ng;
         // 1/(x^n - 1) on the cosets used by the ce domain: x^n = 3^n * w_beta^k, k = kc * beta/ce
         std::vector<HF> zinv(ce);
         { HF on = HF::from_u64(3).pow((u128)n), wb = HF::root_of_unity(log_beta);
           for (uint64_t kc = 0; kc < ce; kc++) zinv[kc] = (on * wb.pow((u128)(kc << (log_beta - log_ce))) - HF::raw(1)).inv(); }
-        // periodic column over the ce domain (PeriodicValueTable): P_L((x)^(n/L)) tabulated on 3^(n/L) * <w_{L*ce}>
+        // periodic column over the ce domain (PeriodicValueTable): P_L(x^(n/L)) tabulated on 3^(n/L) * <w_{L*ce}>
         std::vector<HF> per;
         if (air.id == ZKB_AIR_ID_MIMC) {
             const size_t L = air.params.size();
@@ -402,12 +600,13 @@ struct zkb_ctx {
             for (size_t t = 0; t < L * ce; t++) { HF acc; for (size_t q = L; q-- > 0;) acc = acc * x + poly[q]; per[t] = acc; x = x * wl; }
         }
         // pack the small arrays into one device buffer
-        size_t off_t = 0, off_c = off_t + nt * 16, off_v = off_c + na * 16, off_z = off_v + na * 16, off_p = off_z + ce * 16,
-               off_col = off_p + per.size() * 16, total = off_col + na * 4;
+        const uint32_t ntl = p.n_trans;
+        size_t off_t = 0, off_c = off_t + (size_t)ntl * 16, off_v = off_c + (size_t)nl * 16, off_z = off_v + (size_t)nl * 16, off_p = off_z + ce * 16,
+               off_col = off_p + per.size() * 16, total = off_col + (size_t)nl * 4 + 16;
         std::vector<uint8_t> pack(total);
-        memcpy(&pack[off_t], tcoef.data(), nt * 16); memcpy(&pack[off_c], acoef.data(), na * 16); memcpy(&pack[off_v], aval.data(), na * 16);
+        memcpy(&pack[off_t], tcoef.data() + (windowed ? col0 : 0), (size_t)ntl * 16);
+        if (nl) { memcpy(&pack[off_c], acoef.data(), (size_t)nl * 16); memcpy(&pack[off_v], aval.data(), (size_t)nl * 16); memcpy(&pack[off_col], acol.data(), (size_t)nl * 4); }
         memcpy(&pack[off_z], zinv.data(), ce * 16); if (!per.empty()) memcpy(&pack[off_p], per.data(), per.size() * 16);
-        memcpy(&pack[off_col], acol.data(), na * 4);
         d_aux.ensure(total);
         h2d(d_aux.p, pack.data(), total);
         uint8_t* base = d_aux.as<uint8_t>();
@@ -417,12 +616,29 @@ struct zkb_ctx {
         p.g_last = to_fe(g.pow((u128)(n - 1)));
         p.k = air.id == ZKB_AIR_ID_AGGREGATION ? to_fe(air.params[0]) : fe{};
         p.roots = roots; p.log_tab = log_tab;
-        d_comp_evals.ensure(n * ce * 16);
-        p.out = d_comp_evals.as<fe>();
+        p.out = out;
         const uint64_t threads = n * ce;
         k_eval_constraints<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(p);
         check_launch();
         CK(cudaStreamSynchronize(stream));  // `pack` must outlive the copy
+    }
+    void constraints_eval(const HF& alpha, uint8_t* evals_out) {
+        if (stage != ST_TRACE) throw StateError("zkb_constraints_eval: trace is not committed");
+        CK(cudaEventRecord(ev[0], stream));
+        const uint64_t n = air.n, ce = (uint64_t)1 << log_ce;
+        d_comp_evals.ensure(n * ce * 16);
+        if (!mg_active) {
+            constraints_eval_window(alpha, lde_mat(), 0, air.w, d_comp_evals.as<fe>());
+        } else {
+            // column-sharded: partial evaluation over this rank's columns, all-gather, field sum
+            const uint32_t wl = air.w >> log_g;
+            d_mg_a.ensure(n * ce * 16);
+            d_mg_b.ensure(n * ce * 16 * mg_world);
+            constraints_eval_window(alpha, lde_mat(), mg_rank * wl, wl, d_mg_a.as<fe>());
+            NK(g_nccl.AllGather(d_mg_a.p, d_mg_b.p, n * ce * 16, ncclUint8, comm, stream));
+            k_sum_partials<<<(unsigned)((n * ce + 255) / 256), 256, 0, stream>>>(d_mg_b.as<fe>(), mg_world, n * ce, n * ce, d_comp_evals.as<fe>());
+            check_launch();
+        }
         CK(cudaEventRecord(ev[1], stream));
         if (evals_out) d2h(evals_out, d_comp_evals.p, n * ce * 16);
         CK(cudaEventSynchronize(ev[1]));
@@ -452,7 +668,7 @@ struct zkb_ctx {
             comp_log_p = run_xform(x, d_tmp1, d_tmp2);
         }
         d_comp_tree.ensure(2 * N * 32);
-        k_hash_lde_rows<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(comp_mat(), d_comp_tree.as<uint32_t>() + N * 8);
+        k_hash_lde_rows<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(comp_mat(), d_comp_tree.as<uint32_t>() + N * 8, 0);
         check_launch();
         build_merkle(d_comp_tree.as<uint32_t>(), N);
         CK(cudaEventRecord(ev[1], stream));
@@ -465,43 +681,53 @@ struct zkb_ctx {
         stage = ST_COMP;
     }
 
-    // K7
+    // K7.  Trace polynomials are held per rank for its own columns (all of them on one GPU); a column-sharded proof
+    // all-gathers the 2*w_local evaluations.
     void ood_eval(const HF& z_) {
         if (stage != ST_COMP) throw StateError("zkb_ood_eval: constraint commitment is missing");
         CK(cudaEventRecord(ev[0], stream));
         z = z_; zg = z * HF::root_of_unity(log_n);
         const uint64_t n = air.n; const uint32_t w = air.w;
+        const uint32_t wl = mg_active ? (w >> log_g) : w;   // columns of d_polys
         const uint32_t R = 128;
         const uint32_t nch = (uint32_t)((n + R - 1) / R);
         std::vector<HF> zp(2 * nch);
         { HF zr = z.pow(R), zgr = zg.pow(R), a = HF::raw(1), b = HF::raw(1);
           for (uint32_t q = 0; q < nch; q++) { zp[q] = a; zp[nch + q] = b; a = a * zr; b = b * zgr; } }
-        // layout of d_small: [zpow nch][zgpow nch][part_z nch*w][part_zg nch*w][ood 2w][hpart ...]
+        // layout of d_small: [zpow nch][zgpow nch][part_z nch*wl][part_zg nch*wl][ood 2wl][hpart c*nt][gathered 2w]
         const uint32_t Q = 64;
         const uint32_t nt = (uint32_t)((n + Q - 1) / Q);
-        size_t o_zp = 0, o_pz = o_zp + 2 * (size_t)nch, o_pzg = o_pz + (size_t)nch * w, o_ood = o_pzg + (size_t)nch * w,
-               o_hp = o_ood + 2 * (size_t)w, total = o_hp + (size_t)c * nt;
+        size_t o_zp = 0, o_pz = o_zp + 2 * (size_t)nch, o_pzg = o_pz + (size_t)nch * wl, o_ood = o_pzg + (size_t)nch * wl,
+               o_hp = o_ood + 2 * (size_t)wl, o_ga = o_hp + (size_t)c * nt, total = o_ga + 2 * (size_t)w;
         d_small.ensure(total * 16);
         fe* sm = d_small.as<fe>();
         h2d(sm + o_zp, zp.data(), zp.size() * 16);
-        k_ood_partial<<<nch, 256, 0, stream>>>(d_polys, (uint32_t)n, w, R, to_fe(z), to_fe(zg), sm + o_zp, sm + o_zp + nch, sm + o_pz, sm + o_pzg);
+        k_ood_partial<<<nch, 256, 0, stream>>>(d_polys, (uint32_t)n, wl, R, to_fe(z), to_fe(zg), sm + o_zp, sm + o_zp + nch, sm + o_pz, sm + o_pzg);
         check_launch();
-        k_col_sum<<<(w + 127) / 128, 128, 0, stream>>>(sm + o_pz, nch, w, sm + o_ood);
+        k_col_sum<<<(wl + 127) / 128, 128, 0, stream>>>(sm + o_pz, nch, wl, sm + o_ood);
         check_launch();
-        k_col_sum<<<(w + 127) / 128, 128, 0, stream>>>(sm + o_pzg, nch, w, sm + o_ood + w);
+        k_col_sum<<<(wl + 127) / 128, 128, 0, stream>>>(sm + o_pzg, nch, wl, sm + o_ood + wl);
         check_launch();
-        // H_i(z) from the composition column coefficients (still in d_bufA)
+        // H_i(z) from the composition column coefficients (still in d_bufA; replicated on every rank)
         {
             dim3 grid((nt + 255) / 256, c);
             k_poly_eval_partial<<<grid, 256, 0, stream>>>(d_bufA.as<fe>(), (uint32_t)n, Q, to_fe(z), to_fe(z.pow(Q)), sm + o_hp);
             check_launch();
         }
-        std::vector<HF> host(2 * (size_t)w + (size_t)c * nt);
+        std::vector<HF> host(2 * (size_t)wl + (size_t)c * nt);
         d2h(host.data(), sm + o_ood, host.size() * 16);  // ood and hpart are adjacent
-        ood_cur.assign(host.begin(), host.begin() + w);
-        ood_next.assign(host.begin() + w, host.begin() + 2 * w);
+        ood_cur.assign(w, HF()); ood_next.assign(w, HF());
+        if (!mg_active) {
+            for (uint32_t j = 0; j < w; j++) { ood_cur[j] = host[j]; ood_next[j] = host[w + j]; }
+        } else {
+            NK(g_nccl.AllGather(sm + o_ood, sm + o_ga, 2 * (size_t)wl * 16, ncclUint8, comm, stream));
+            std::vector<HF> all(2 * (size_t)w);
+            d2h(all.data(), sm + o_ga, all.size() * 16);
+            for (int r = 0; r < mg_world; r++)
+                for (uint32_t jl = 0; jl < wl; jl++) { ood_cur[r * wl + jl] = all[(size_t)r * 2 * wl + jl]; ood_next[r * wl + jl] = all[(size_t)r * 2 * wl + wl + jl]; }
+        }
         ood_h.assign(c, HF());
-        for (uint32_t i = 0; i < c; i++) { HF s; for (uint32_t t = 0; t < nt; t++) s = s + host[2 * (size_t)w + (size_t)i * nt + t]; ood_h[i] = s; }
+        for (uint32_t i = 0; i < c; i++) { HF s_; for (uint32_t t = 0; t < nt; t++) s_ = s_ + host[2 * (size_t)wl + (size_t)i * nt + t]; ood_h[i] = s_; }
         CK(cudaEventRecord(ev[1], stream));
         CK(cudaEventSynchronize(ev[1]));
         CK(cudaEventElapsedTime(&times.ood, ev[0], ev[1]));
@@ -523,9 +749,24 @@ struct zkb_ctx {
         d_aux.ensure((w + c) * 16);
         h2d(d_aux.p, g.data(), g.size() * 16);
         d_ab.ensure(n * 2 * 16);
-        k_deep_combine<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(d_polys, (uint32_t)n, w, d_aux.as<fe>(), d_bufA.as<fe>(), c,
-                                                                          d_aux.as<fe>() + w, d_ab.as<fe>());
-        check_launch();
+        if (!mg_active) {
+            k_deep_combine<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(d_polys, (uint32_t)n, w, d_aux.as<fe>(), d_bufA.as<fe>(), c,
+                                                                              d_aux.as<fe>() + w, d_ab.as<fe>());
+            check_launch();
+        } else {
+            // partial A over this rank's columns -> all-gather -> field sum -> add the (replicated) H part
+            const uint32_t wl = w >> log_g;
+            d_mg_a.ensure(n * 2 * 16);
+            d_mg_b.ensure(n * 2 * 16 * mg_world);
+            k_deep_combine<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(d_polys, (uint32_t)n, wl, d_aux.as<fe>() + (size_t)mg_rank * wl,
+                                                                              d_bufA.as<fe>(), 0, d_aux.as<fe>() + w, d_mg_a.as<fe>());
+            check_launch();
+            NK(g_nccl.AllGather(d_mg_a.p, d_mg_b.p, n * 2 * 16, ncclUint8, comm, stream));
+            k_sum_partials<<<(unsigned)((2 * n + 255) / 256), 256, 0, stream>>>(d_mg_b.as<fe>(), mg_world, 2 * n, 2 * n, d_ab.as<fe>());
+            check_launch();
+            k_deep_add_h<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_ab.as<fe>(), (uint32_t)n, d_bufA.as<fe>(), c, d_aux.as<fe>() + w);
+            check_launch();
+        }
         CK(cudaStreamSynchronize(stream));  // `g` must outlive the copy
         d_ab_lde.ensure(N * 2 * 16);
         {
@@ -624,6 +865,7 @@ struct zkb_ctx {
     void query(uint32_t which, const std::vector<uint32_t>& pos, std::vector<uint8_t>& rows, std::vector<uint8_t>& paths) {
         const uint32_t np = (uint32_t)pos.size();
         if (np == 0 || np > 255) throw InvalidArg("bad number of query positions");
+        if (which == 0 && mg_active) { query_trace_mg(pos, rows, paths); return; }
         uint32_t width, depth; const uint32_t* heap;
         uint64_t domain;
         if (which == 0) { width = air.w; domain = air.lde_size(); heap = d_tree.as<uint32_t>(); }
@@ -667,11 +909,16 @@ struct zkb_ctx {
 
     // ==========================================================================================================
     // Prover::prove: the whole pipeline with the channel on the host  
-    std::vector<uint8_t> prove(const zkb_air_desc* desc, const uint8_t* const* cols, const fe* d_trace_in, uint64_t force_nonce) {
+    // sharded = true: `cols` / `d_trace_in` hold only this rank's w/G columns and the proof is produced cooperatively by all
+    // ranks of the NCCL communicator (every rank returns the same bytes)
+    std::vector<uint8_t> prove(const zkb_air_desc* desc, const uint8_t* const* cols, const fe* d_trace_in, uint64_t force_nonce,
+                               bool sharded = false) {
         begin(desc);
         CK(cudaEventRecord(ev[14], stream));
         uint8_t root[32];
-        if (d_trace_in) trace_commit_device(d_trace_in, root); else trace_commit_host(cols, root);
+        if (sharded) trace_commit_mg(cols, d_trace_in, root);
+        else if (d_trace_in) trace_commit_device(d_trace_in, root);
+        else trace_commit_host(cols, root);
         coin.reseed(root);                                   // channel.commit_trace
         HF alpha = coin.draw();                              // get_constraint_composition_coeffs
         alpha.to_bytes(ts.constraint_alpha);
@@ -868,6 +1115,41 @@ int32_t zkb_query(zkb_ctx* ctx, uint32_t which, const uint32_t* positions, uint3
         if (rows_out) memcpy(rows_out, rows.data(), rows.size());
         if (proof_len) *proof_len = paths.size();
         if (proof_out) *proof_out = dup_bytes(paths);
+    });
+}
+
+int32_t zkb_mg_unique_id(uint8_t out[128]) {
+    try {
+        if (!out) throw InvalidArg("null output");
+        g_nccl.load();
+        ncclUniqueId id;
+        NK(g_nccl.GetUniqueId(&id));
+        memcpy(out, &id, 128);
+        return ZKB_OK;
+    } catch (const InvalidArg& e) { g_last_error = e.what(); return ZKB_ERR_INVALID; }
+    catch (const std::exception& e) { g_last_error = e.what(); return ZKB_ERR_CUDA; }
+}
+int32_t zkb_mg_init(zkb_ctx* ctx, int32_t rank, int32_t world, const uint8_t id[128]) {
+    return guarded(ctx, [&] { if (!id) throw InvalidArg("null NCCL id"); ctx->mg_init(rank, world, id); });
+}
+int32_t zkb_mg_prove(zkb_ctx* ctx, const zkb_air_desc* air, const uint8_t* const* local_cols, uint64_t force_nonce, uint8_t** proof_out,
+                     uint64_t* proof_len, zkb_transcript* transcript) {
+    return guarded(ctx, [&] {
+        if (!local_cols) throw InvalidArg("null trace columns");
+        std::vector<uint8_t> b = ctx->prove(air, local_cols, nullptr, force_nonce, true);
+        if (transcript) *transcript = ctx->ts;
+        if (proof_len) *proof_len = b.size();
+        if (proof_out) *proof_out = dup_bytes(b);
+    });
+}
+int32_t zkb_mg_prove_device(zkb_ctx* ctx, const zkb_air_desc* air, const void* d_local_trace, uint64_t force_nonce, uint8_t** proof_out,
+                            uint64_t* proof_len, zkb_transcript* transcript) {
+    return guarded(ctx, [&] {
+        if (!d_local_trace) throw InvalidArg("null device trace");
+        std::vector<uint8_t> b = ctx->prove(air, nullptr, (const fe*)d_local_trace, force_nonce, true);
+        if (transcript) *transcript = ctx->ts;
+        if (proof_len) *proof_len = b.size();
+        if (proof_out) *proof_out = dup_bytes(b);
     });
 }
 

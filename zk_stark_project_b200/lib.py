@@ -77,9 +77,18 @@ EXPORTS = [
     "zkb_host_free", "zkb_prove", "zkb_prove_device", "zkb_free", "zkb_begin", "zkb_trace_commit", "zkb_trace_commit_device",
     "zkb_trace_read_frame", "zkb_trace_polys_read", "zkb_constraints_eval", "zkb_constraints_commit", "zkb_ood_eval",
     "zkb_deep_compose", "zkb_fri_num_layers", "zkb_fri_commit_layer", "zkb_fri_fold", "zkb_fri_remainder", "zkb_grind",
-    "zkb_query", "zkb_mimc_trace", "zkb_mimc_trace_device", "zkb_upload_trace", "zkb_test_field", "zkb_test_hash_elements",
+    "zkb_query", "zkb_mg_unique_id", "zkb_mg_init", "zkb_mg_prove", "zkb_mg_prove_device", "zkb_mimc_trace", "zkb_mimc_trace_device", "zkb_upload_trace", "zkb_test_field", "zkb_test_hash_elements",
     "zkb_test_merkle_root", "zkb_test_lde",
 ]
+
+
+def mg_unique_id():
+    """ncclGetUniqueId (call on rank 0 and broadcast the 128 bytes)."""
+    buf = C.create_string_buffer(128)
+    rc = load().zkb_mg_unique_id(buf)
+    if rc != 0:
+        raise ZkbError(rc, load().zkb_last_error(None).decode())
+    return buf.raw
 
 
 def fe_bytes(x):
@@ -170,6 +179,29 @@ class Context:
         out, ln, ts = C.c_void_p(), C.c_uint64(), Transcript()
         self.check(self.lib.zkb_prove_device(self.handle, C.byref(d), C.c_void_p(d_trace), C.c_uint64(force_nonce), C.byref(out),
                                              C.byref(ln), C.byref(ts)))
+        proof = C.string_at(out, ln.value)
+        self.lib.zkb_free(out)
+        return proof, ts
+
+    # ---- column-sharded single proof ----
+    def mg_init(self, rank, world, unique_id):
+        self.check(self.lib.zkb_mg_init(self.handle, C.c_int32(rank), C.c_int32(world), unique_id))
+
+    def mg_prove_host(self, air, local_trace_ptr, world, force_nonce=0):
+        """air: description of the WHOLE trace; local_trace_ptr: this rank's w/world columns, column-major."""
+        d = self.prepare(air)
+        out, ln, ts = C.c_void_p(), C.c_uint64(), Transcript()
+        cols = self._col_ptrs(local_trace_ptr, d.trace_width // world, d.trace_len)
+        self.check(self.lib.zkb_mg_prove(self.handle, C.byref(d), cols, C.c_uint64(force_nonce), C.byref(out), C.byref(ln), C.byref(ts)))
+        proof = C.string_at(out, ln.value)
+        self.lib.zkb_free(out)
+        return proof, ts
+
+    def mg_prove_device(self, air, d_local_trace, force_nonce=0):
+        d = self.prepare(air)
+        out, ln, ts = C.c_void_p(), C.c_uint64(), Transcript()
+        self.check(self.lib.zkb_mg_prove_device(self.handle, C.byref(d), C.c_void_p(d_local_trace), C.c_uint64(force_nonce), C.byref(out),
+                                                C.byref(ln), C.byref(ts)))
         proof = C.string_at(out, ln.value)
         self.lib.zkb_free(out)
         return proof, ts
