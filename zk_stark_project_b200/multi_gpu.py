@@ -51,3 +51,47 @@ def prove_batch(provers_and_traces, ctx, rank=0, world_size=1, dist=None):
 
 def digest(proof):
     return hashlib.sha256(proof).hexdigest()
+
+
+# ---- column-sharded single proof (BASELINE.json configs[4]): index logic shared by the C++ driver and its tests ---------
+def column_shard(width, world_size, rank):
+    """Columns [r*w/G, (r+1)*w/G) of rank r; G and w/G must be powers of two (zkb_mg_prove)."""
+    if width % world_size or (width // world_size) & (width // world_size - 1) or world_size & (world_size - 1):
+        raise ValueError("width/world_size and world_size must be powers of two")
+    wl = width // world_size
+    return range(rank * wl, (rank + 1) * wl)
+
+
+def row_shard(lde_size, world_size, rank):
+    """LDE rows (= Merkle leaves) [q*N/G, (q+1)*N/G) hashed by rank q after the all-to-all."""
+    nl = lde_size // world_size
+    return range(rank * nl, (rank + 1) * nl)
+
+
+def node_owner(heap_index, lde_size, world_size):
+    """Owner of Merkle heap node `heap_index` (root = 1, leaves = N..2N-1): -1 for the replicated cap (top log2 G levels),
+    else (rank, index in that rank's local subtree heap)."""
+    log_g = world_size.bit_length() - 1
+    d = heap_index.bit_length() - 1
+    if d <= log_g:
+        return -1, heap_index
+    off = heap_index - (1 << d)
+    return off >> (d - log_g), (1 << (d - log_g)) + (off & ((1 << (d - log_g)) - 1))
+
+
+def finish_cap(subtree_roots, merge):
+    """Top log2 G levels from the all-gathered subtree roots; returns the heap (cap[1] = root)."""
+    g = len(subtree_roots)
+    cap = [None] * (2 * g)
+    cap[g:] = list(subtree_roots)
+    for i in range(g - 1, 0, -1):
+        cap[i] = merge(cap[2 * i], cap[2 * i + 1])
+    return cap
+
+
+def init_sharded(ctx, rank, world_size, dist):
+    """Create the library's NCCL communicator: rank 0 draws the id, torch.distributed broadcasts it (control plane only)."""
+    from . import lib
+    ids = [lib.mg_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    ctx.mg_init(rank, world_size, ids[0])
