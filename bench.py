@@ -20,6 +20,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION in this image) off it
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 import numpy as np  # noqa: E402
 
@@ -294,6 +297,8 @@ def main():
         stages = {k_: v_ / args.steps for k_, v_ in stage_acc.items()}
         # interpolation (K1) and the coset LDE (K2) are interleaved per column group inside the library and timed together
         alg["lde"] += alg["interp"]
+        if sharded:  # this rank transforms w/G columns
+            alg["lde"] //= world
         lde_ms = max(stages.get("lde", 0.0), 1e-6)
         achieved = alg["lde"] / (lde_ms * 1e-3) / 1e9
         # per-stage achieved bandwidth against the same peak, for the profile notes

@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(256) k_merkle_level(const uint32_t* __restrict
 // K5: DefaultConstraintEvaluator::evaluate (src/training/prover.rs:283-290) fused with
 // ConstraintEvaluationTable::combine: one thread per constraint-evaluation-domain point.
 enum { ZKB_AIR_TRAINING = 1, ZKB_AIR_AGGREGATION = 2, ZKB_AIR_MIMC = 3 };
-#define ZKB_MAX_GROUPS 8
+#define ZKB_MAX_GROUPS 4
 struct EvalParams {
     LdeMat lde;
     uint32_t air_id, log_ce;      // ce blowup = 2^log_ce
@@ -319,82 +319,101 @@ struct EvalParams {
     fe* out;                      // composition trace, natural ce-domain order
 };
 
+// Each thread evaluates RPT points and shares ONE field inversion (Montgomery batch trick) between all their
+// boundary-divisor denominators: an inversion is ~250 multiplications, as much as the rest of a row's work.
+// RPT is picked by the host: 8 for large domains, 1 when the domain is too small to fill the GPU otherwise.
+template <int ZKB_EVAL_RPT>
 __global__ void __launch_bounds__(128) k_eval_constraints(const EvalParams p) {
     const LdeMat& m = p.lde;
-    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >> (m.log_n + p.log_ce)) return;
+    const uint64_t total = (uint64_t)1 << (m.log_n + p.log_ce);
+    const uint64_t nthreads = total / ZKB_EVAL_RPT;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= nthreads) return;
     const uint32_t lpf = lde_full_log_p(m), lt = m.log_n - lpf;
-    const uint32_t slot = (uint32_t)gid & ((1u << lpf) - 1u);
-    const uint32_t t_low = (uint32_t)(gid >> lpf) & ((1u << lt) - 1u);
-    const uint32_t kc = (uint32_t)(gid >> m.log_n);
-    const uint32_t k = kc << (m.log_beta - p.log_ce);
-    const uint32_t i = t_low + (slot << lt);
-    const uint32_t i1 = (i + 1u) & ((1u << m.log_n) - 1u);  // frame.next = row + blowup (mod N)
-    const uint32_t ci = (i << p.log_ce) + kc;
     const uint32_t log_N = m.log_n + m.log_beta;
-    const uint32_t r = (i << m.log_beta) + k;
-    const fe* cur = m.data + lde_row_base(m, k, i);   // send view / single GPU: columns are local, stride 2^log_p
-    const fe* nxt = m.data + lde_row_base(m, k, i1);
     const size_t cs = (size_t)1 << m.log_p;  // column stride
+    const uint32_t ng = p.n_groups;
 
-    // x = 3 * w_N^r
-    fe x = powtab(p.roots, r << (p.log_tab - log_N));
-    { fe x2 = fe_add(x, x); x = fe_add(x2, x); }
-
-    // transition constraints, merged with their coefficients
-    fe t = fe_zero();
-    if (p.air_id == ZKB_AIR_AGGREGATION) {
-        const uint32_t d = p.n_trans;
-        for (uint32_t c = 0; c < d; c++) {
-            fe dn = fe_sub(fe_load(nxt + c * cs), fe_load(cur + c * cs));
-            fe ev = fe_sub(fe_mul(p.k, dn), fe_load(nxt + (size_t)(c + d) * cs));
-            t = fe_add(t, fe_mul(fe_ldg(p.tcoef + c), ev));
-        }
-    } else if (p.air_id == ZKB_AIR_MIMC) {
-        const fe rc = fe_ldg(p.periodic + (ci & p.per_mask));
-        for (uint32_t c = 0; c < p.n_trans; c++) {
-            fe a1 = fe_add(fe_load(cur + c * cs), rc);
-            fe a2 = fe_sqr(a1), a4 = fe_sqr(a2), a6 = fe_mul(a4, a2), a7 = fe_mul(a6, a1);
-            fe ev = fe_sub(fe_load(nxt + c * cs), a7);
-            t = fe_add(t, fe_mul(fe_ldg(p.tcoef + c), ev));
-        }
-    }  // TRAINING: every transition evaluation is zero (src/training/air.rs:274-278, src/helper.rs:141-146)
-
-    // boundary groups: sum coef * (cur[col] - value), divided by (x - g^step)
-    fe num[ZKB_MAX_GROUPS], den[ZKB_MAX_GROUPS], pre[ZKB_MAX_GROUPS];
+    fe num[ZKB_EVAL_RPT * ZKB_MAX_GROUPS], den[ZKB_EVAL_RPT * ZKB_MAX_GROUPS], pre[ZKB_EVAL_RPT * ZKB_MAX_GROUPS];
+    fe tpart[ZKB_EVAL_RPT];
+    uint32_t cidx[ZKB_EVAL_RPT];
     fe acc = fe_one();
-    for (uint32_t g = 0; g < p.n_groups; g++) {
-        fe s = fe_zero();
-        for (uint32_t a = p.g_off[g]; a < p.g_off[g + 1]; a++) {
-            fe v = fe_sub(fe_load(cur + (size_t)__ldg(p.a_col + a) * cs), fe_ldg(p.a_val + a));
-            s = fe_add(s, fe_mul(fe_ldg(p.a_coef + a), v));
+    for (int s = 0; s < ZKB_EVAL_RPT; s++) {
+        const uint64_t gid = tid + (uint64_t)s * nthreads;
+        const uint32_t slot = (uint32_t)gid & ((1u << lpf) - 1u);
+        const uint32_t t_low = (uint32_t)(gid >> lpf) & ((1u << lt) - 1u);
+        const uint32_t kc = (uint32_t)(gid >> m.log_n);
+        const uint32_t k = kc << (m.log_beta - p.log_ce);
+        const uint32_t i = t_low + (slot << lt);
+        const uint32_t i1 = (i + 1u) & ((1u << m.log_n) - 1u);  // frame.next = row + blowup (mod N)
+        const uint32_t ci = (i << p.log_ce) + kc;
+        const uint32_t r = (i << m.log_beta) + k;
+        cidx[s] = ci;
+        const fe* cur = m.data + lde_row_base(m, k, i);   // send view / single GPU: columns are local, stride 2^log_p
+        const fe* nxt = m.data + lde_row_base(m, k, i1);
+
+        // x = 3 * w_N^r
+        fe x = powtab(p.roots, r << (p.log_tab - log_N));
+        { fe x2 = fe_add(x, x); x = fe_add(x2, x); }
+
+        // transition constraints, merged with their coefficients
+        fe t = fe_zero();
+        if (p.air_id == ZKB_AIR_AGGREGATION) {
+            const uint32_t d = p.n_trans;
+            for (uint32_t c = 0; c < d; c++) {
+                fe dn = fe_sub(fe_load(nxt + c * cs), fe_load(cur + c * cs));
+                fe ev = fe_sub(fe_mul(p.k, dn), fe_load(nxt + (size_t)(c + d) * cs));
+                t = fe_add(t, fe_mul(fe_ldg(p.tcoef + c), ev));
+            }
+        } else if (p.air_id == ZKB_AIR_MIMC) {
+            const fe rc = fe_ldg(p.periodic + (ci & p.per_mask));
+            for (uint32_t c = 0; c < p.n_trans; c++) {
+                fe a1 = fe_add(fe_load(cur + c * cs), rc);
+                fe a2 = fe_sqr(a1), a4 = fe_sqr(a2), a6 = fe_mul(a4, a2), a7 = fe_mul(a6, a1);
+                fe ev = fe_sub(fe_load(nxt + c * cs), a7);
+                t = fe_add(t, fe_mul(fe_ldg(p.tcoef + c), ev));
+            }
+        }  // TRAINING: every transition evaluation is zero (src/training/air.rs:274-278, src/helper.rs:141-146)
+        tpart[s] = fe_mul(fe_mul(t, fe_sub(x, p.g_last)), fe_ldg(p.zinv + kc));
+
+        // boundary groups: sum coef * (cur[col] - value), to be divided by (x - g^step)
+        for (uint32_t g = 0; g < ng; g++) {
+            fe sum = fe_zero();
+            for (uint32_t a = p.g_off[g]; a < p.g_off[g + 1]; a++) {
+                fe v = fe_sub(fe_load(cur + (size_t)__ldg(p.a_col + a) * cs), fe_ldg(p.a_val + a));
+                sum = fe_add(sum, fe_mul(fe_ldg(p.a_coef + a), v));
+            }
+            const uint32_t q = s * ZKB_MAX_GROUPS + g;
+            num[q] = sum;
+            den[q] = fe_sub(x, p.g_point[g]);
+            pre[q] = acc;
+            acc = fe_mul(acc, den[q]);
         }
-        num[g] = s;
-        den[g] = fe_sub(x, p.g_point[g]);
-        pre[g] = acc;
-        acc = fe_mul(acc, den[g]);
     }
-    fe res = fe_mul(fe_mul(t, fe_sub(x, p.g_last)), fe_ldg(p.zinv + kc));
-    if (p.n_groups) {
-        fe ia = fe_inv(acc);
-        for (int g = (int)p.n_groups - 1; g >= 0; g--) {
-            fe di = fe_mul(ia, pre[g]);
-            ia = fe_mul(ia, den[g]);
-            res = fe_add(res, fe_mul(num[g], di));
+    fe ia = ng ? fe_inv(acc) : fe_one();
+    for (int s = ZKB_EVAL_RPT - 1; s >= 0; s--) {
+        fe res = tpart[s];
+        for (int g = (int)ng - 1; g >= 0; g--) {
+            const uint32_t q = s * ZKB_MAX_GROUPS + g;
+            fe di = fe_mul(ia, pre[q]);
+            ia = fe_mul(ia, den[q]);
+            res = fe_add(res, fe_mul(num[q], di));
         }
+        fe_store(p.out + cidx[s], res);
     }
-    fe_store(p.out + ci, res);
 }
 
 // ------------------------------------------------------------------------------------------------
 // K7: TracePolyTable::get_ood_frame — T_j(z), T_j(z*g) for all columns (inside Prover::prove)
 // polys row-major [n][w]; block c handles rows [c*R, (c+1)*R), thread j handles column j.
-__global__ void __launch_bounds__(256) k_ood_partial(const fe* __restrict__ polys, uint32_t n, uint32_t w, uint32_t R,
+// A block of 256 threads = nsub row-chunks x wq columns (wq = power of two >= w); chunk q covers rows [q*R, (q+1)*R).
+__global__ void __launch_bounds__(256) k_ood_partial(const fe* __restrict__ polys, uint32_t n, uint32_t w, uint32_t R, uint32_t log_wq,
                                                       fe z, fe zg, const fe* __restrict__ zpow, const fe* __restrict__ zgpow,
                                                       fe* __restrict__ part_z, fe* __restrict__ part_zg) {
-    const uint32_t j = threadIdx.x, c = blockIdx.x;
-    if (j >= w) return;
+    const uint32_t j = threadIdx.x & ((1u << log_wq) - 1u), sub = threadIdx.x >> log_wq;
+    const uint32_t c = blockIdx.x * (256u >> log_wq) + sub;
     const uint32_t m0 = c * R;
+    if (j >= w || m0 >= n) return;
     const uint32_t m1 = min(n, m0 + R);
     fe a = fe_zero(), b = fe_zero();
     for (uint32_t m = m1; m-- > m0;) {
@@ -405,13 +424,25 @@ __global__ void __launch_bounds__(256) k_ood_partial(const fe* __restrict__ poly
     fe_store(part_z + (size_t)c * w + j, fe_mul(a, fe_ldg(zpow + c)));
     fe_store(part_zg + (size_t)c * w + j, fe_mul(b, fe_ldg(zgpow + c)));
 }
-// out[j] = sum_c part[c][j]
-__global__ void k_col_sum(const fe* __restrict__ part, uint32_t nchunks, uint32_t w, fe* __restrict__ out) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= w) return;
+// out[j] = sum_c part[c][j]; block = 32 columns x 32 chunk lanes, tree-reduced in shared memory
+__global__ void __launch_bounds__(1024) k_col_sum(const fe* __restrict__ part, uint32_t nchunks, uint32_t w, fe* __restrict__ out) {
+    __shared__ uint4 red[32][33];
+    const uint32_t jx = threadIdx.x, gy = threadIdx.y;
+    const uint32_t j = blockIdx.x * 32 + jx;
     fe s = fe_zero();
-    for (uint32_t c = 0; c < nchunks; c++) s = fe_add(s, fe_load(part + (size_t)c * w + j));
-    fe_store(out + j, s);
+    if (j < w) for (uint32_t c = gy; c < nchunks; c += 32) s = fe_add(s, fe_load(part + (size_t)c * w + j));
+    red[gy][jx] = make_uint4(s.x[0], s.x[1], s.x[2], s.x[3]);
+    __syncthreads();
+    for (uint32_t h = 16; h > 0; h >>= 1) {
+        if (gy < h) {
+            uint4 o = red[gy + h][jx];
+            fe t; t.x[0] = o.x; t.x[1] = o.y; t.x[2] = o.z; t.x[3] = o.w;
+            s = fe_add(s, t);
+            red[gy][jx] = make_uint4(s.x[0], s.x[1], s.x[2], s.x[3]);
+        }
+        __syncthreads();
+    }
+    if (gy == 0 && j < w) fe_store(out + j, s);
 }
 // CompositionPoly::evaluate_at: H_i(z) for contiguous coefficient columns [c][n]; one block per column chunk
 __global__ void __launch_bounds__(256) k_poly_eval_partial(const fe* __restrict__ coef, uint32_t n, uint32_t Q, fe z, fe zQ,

@@ -133,7 +133,7 @@ struct zkb_ctx {
     int mg_rank = 0, mg_world = 1;
     uint32_t log_g = 0;
     bool mg_active = false;             // the proof in flight is sharded
-    DevBuf d_lde_rows, d_mg_a, d_mg_b;  // recv view of the LDE; all-gather staging
+    DevBuf d_lde_rows, d_mg_a, d_mg_b, d_comp_rm;  // recv view of the LDE; all-gather staging
     std::vector<Digest32> mg_cap;       // heap of the replicated top log G levels: cap[1] = root, cap[G + q] = subtree root q
 
     // ==========================================================================================================
@@ -176,7 +176,7 @@ struct zkb_ctx {
         cudaStreamSynchronize(stream);
         for (DevBuf* b : {&d_trace, &d_bufA, &d_bufB, &d_tmp1, &d_tmp2, &d_lde, &d_tree, &d_small, &d_comp_evals, &d_comp_lde, &d_comp_tree,
                           &d_ab, &d_ab_lde, &d_deep, &d_roots_lo, &d_roots_hi, &d_inv3_lo, &d_inv3_hi, &d_pow3, &d_aux, &d_gather, &d_user_trace,
-                          &d_lde_rows, &d_mg_a, &d_mg_b})
+                          &d_lde_rows, &d_mg_a, &d_mg_b, &d_comp_rm})
             b->release();
         if (comm) { g_nccl.CommDestroy(comm); comm = nullptr; }
         for (auto& b : d_fri_evals) b.release();
@@ -617,8 +617,11 @@ struct zkb_ctx {
         p.k = air.id == ZKB_AIR_ID_AGGREGATION ? to_fe(air.params[0]) : fe{};
         p.roots = roots; p.log_tab = log_tab;
         p.out = out;
-        const uint64_t threads = n * ce;
-        k_eval_constraints<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(p);
+        // rows per thread: share one inversion between 8 points once there are enough points to fill the GPU anyway
+        const uint64_t points = n * ce;  // n >= 8 and ce >= 2: always a multiple of 8
+        if (points >= ((uint64_t)1 << 21)) k_eval_constraints<8><<<(unsigned)((points / 8 + 127) / 128), 128, 0, stream>>>(p);
+        else if (points >= ((uint64_t)1 << 19)) k_eval_constraints<2><<<(unsigned)((points / 2 + 127) / 128), 128, 0, stream>>>(p);
+        else k_eval_constraints<1><<<(unsigned)((points + 127) / 128), 128, 0, stream>>>(p);
         check_launch();
         CK(cudaStreamSynchronize(stream));  // `pack` must outlive the copy
     }
@@ -663,6 +666,7 @@ struct zkb_ctx {
         }
         // evaluate the c column polynomials over the LDE domain (panel layout, width c)
         d_comp_lde.ensure(N * c * 16);
+        // (measured: c single-column transforms with 4096-point tiles beat one 8-wide batch, which needs a third pass)
         for (uint32_t i = 0; i < c; i++) {
             Xform x{coef + (size_t)i * n, 1, 0, d_comp_lde.as<fe>(), c, i, 1, log_n, false, true, log_N, false, HF()};
             comp_log_p = run_xform(x, d_tmp1, d_tmp2);
@@ -689,8 +693,10 @@ struct zkb_ctx {
         z = z_; zg = z * HF::root_of_unity(log_n);
         const uint64_t n = air.n; const uint32_t w = air.w;
         const uint32_t wl = mg_active ? (w >> log_g) : w;   // columns of d_polys
-        const uint32_t R = 128;
+        const uint32_t R = 64;
         const uint32_t nch = (uint32_t)((n + R - 1) / R);
+        uint32_t log_wq = 0; while ((1u << log_wq) < wl) log_wq++;
+        const uint32_t nsub = 256u >> log_wq;
         std::vector<HF> zp(2 * nch);
         { HF zr = z.pow(R), zgr = zg.pow(R), a = HF::raw(1), b = HF::raw(1);
           for (uint32_t q = 0; q < nch; q++) { zp[q] = a; zp[nch + q] = b; a = a * zr; b = b * zgr; } }
@@ -702,11 +708,12 @@ struct zkb_ctx {
         d_small.ensure(total * 16);
         fe* sm = d_small.as<fe>();
         h2d(sm + o_zp, zp.data(), zp.size() * 16);
-        k_ood_partial<<<nch, 256, 0, stream>>>(d_polys, (uint32_t)n, wl, R, to_fe(z), to_fe(zg), sm + o_zp, sm + o_zp + nch, sm + o_pz, sm + o_pzg);
+        k_ood_partial<<<(nch + nsub - 1) / nsub, 256, 0, stream>>>(d_polys, (uint32_t)n, wl, R, log_wq, to_fe(z), to_fe(zg), sm + o_zp, sm + o_zp + nch,
+                                                                   sm + o_pz, sm + o_pzg);
         check_launch();
-        k_col_sum<<<(wl + 127) / 128, 128, 0, stream>>>(sm + o_pz, nch, wl, sm + o_ood);
+        k_col_sum<<<(wl + 31) / 32, dim3(32, 32), 0, stream>>>(sm + o_pz, nch, wl, sm + o_ood);
         check_launch();
-        k_col_sum<<<(wl + 127) / 128, 128, 0, stream>>>(sm + o_pzg, nch, wl, sm + o_ood + wl);
+        k_col_sum<<<(wl + 31) / 32, dim3(32, 32), 0, stream>>>(sm + o_pzg, nch, wl, sm + o_ood + wl);
         check_launch();
         // H_i(z) from the composition column coefficients (still in d_bufA; replicated on every rank)
         {
