@@ -211,3 +211,59 @@ def test_column_sharded_proof_two_gpus():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29611", "tests/mg_worker.py", cases], cwd=root, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "mg ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def _training_shaped(oracle, gpu_ctx, w, n, opts, seed):
+    data = T.random_felts(w * n, seed).reshape(w, n, 2)
+    air = T.synthetic_training_air(n, opts, data)
+    return _prove_both(gpu_ctx, oracle, air, Z.TraceTable(data))
+
+
+@pytest.mark.parametrize("w,n,blowup", [(2, 8, 2), (2, 8, 16), (4, 16, 4), (254, 16, 8), (6, 32, 32), (10, 64, 64), (2, 8, 128), (30, 2048, 2)])
+def test_edge_shapes_training_air(gpu_ctx, oracle, w, n, blowup):
+    """Minimum trace length (TraceInfo: n >= 8), extreme widths, every blowup factor ProofOptions accepts (2..128),
+    domains small enough that FRI has zero layers (N <= 128: the remainder is interpolated straight from the DEEP evaluations)."""
+    _training_shaped(oracle, gpu_ctx, w, n, Z.ProofOptions(27, blowup, 6, Z.FieldExtension.NONE, 16, 7), 31 * w + n)
+
+
+@pytest.mark.parametrize("queries,grinding,rem", [(1, 0, 7), (255, 3, 7), (40, 10, 0), (40, 4, 3), (40, 4, 15), (12, 32 - 16, 31)])
+def test_option_extremes(gpu_ctx, oracle, queries, grinding, rem):
+    """num_queries 1 and 255, no grinding, remainder degrees 0..31 (FRI depth changes with the remainder bound)."""
+    opts = Z.ProofOptions(queries, 16, grinding, Z.FieldExtension.NONE, 16, rem)
+    # with remainder degree 0 FRI folds all the way to a constant: the trace length must be a power of the folding factor
+    # or the verifier reports degree truncation (as Winterfell's does)
+    n = 4096 if rem == 0 else 1024
+    _training_shaped(oracle, gpu_ctx, 8, n, opts, 77 + queries)
+
+
+def test_mimc_width_255_like(gpu_ctx, oracle):
+    """Widest MiMC trace that still fits TraceInfo (255 columns: 4 BLAKE3 chunks per leaf with a ragged tail)."""
+    p = T.mimc_prover(255, 64, T.options(blowup=8))
+    trace = p.build_trace()
+    _prove_both(gpu_ctx, oracle, p.describe(trace), trace)
+
+
+def test_repeated_proofs_reuse_context(gpu_ctx, oracle):
+    """A context is reused across proofs of different shapes (buffers grow, tables are rebuilt); results stay exact."""
+    for width, steps, blowup in [(4, 4096, 8), (2, 64, 16), (16, 512, 8), (4, 4096, 8)]:
+        p = T.mimc_prover(width, steps, T.options(blowup=blowup))
+        raw = oracle.mimc_trace(p.seeds, steps, p.rc)
+        trace = Z.TraceTable(np.frombuffer(raw, dtype=np.uint64).reshape(width, steps, 2))
+        _prove_both(gpu_ctx, oracle, p.describe(trace), trace)
+
+
+def test_pageable_and_scattered_columns(gpu_ctx, oracle):
+    """Columns handed over as separate, non-contiguous, pageable host buffers (what a Vec<Vec<Felt>> TraceTable looks like)."""
+    p = T.aggregation_prover(16, T.options())
+    trace = p.build_trace()
+    air = p.describe(trace)
+    w, n = trace.width(), trace.length()
+    cols = [np.array(trace.data[j], copy=True) for j in reversed(range(w))][::-1]  # separately allocated
+    ptrs = (C.c_void_p * w)(*[c.ctypes.data for c in cols])
+    d = L.make_desc(air)
+    out, ln, ts = C.c_void_p(), C.c_uint64(), L.Transcript()
+    gpu_ctx.check(gpu_ctx.lib.zkb_prove(gpu_ctx.handle, C.byref(d), ptrs, C.c_uint64(0), C.byref(out), C.byref(ln), C.byref(ts)))
+    proof = C.string_at(out, ln.value)
+    gpu_ctx.lib.zkb_free(out)
+    ref, _, _ = oracle.prove(air, trace.to_bytes())
+    assert proof == ref
