@@ -41,17 +41,26 @@ static inline int ilog2(size_t n) { int l = 0; while (((size_t)1 << l) < n) l++;
 // winter-math `fft`: only the mathematical contracts matter for parity
 //   interpolate_poly(evals over <w_n>)            -> coefficients
 //   evaluate_poly_with_offset(p, offset, blowup)  -> [p(offset * w_N^i)] natural order
-static inline void fft_in_place(Fe* a, size_t n, Fe root) {
-    // iterative radix-2 DIT, natural in / natural out
-    int ln = ilog2(n);
-    for (size_t i = 0; i < n; i++) {
-        size_t j = 0;
-        for (int b = 0; b < ln; b++) if (i >> b & 1) j |= (size_t)1 << (ln - 1 - b);
-        if (i < j) std::swap(a[i], a[j]);
-    }
+// twiddles w^0 .. w^(n/2-1), cached per (n, root) and per thread (winter-math precomputes them once per domain too)
+static inline const std::vector<Fe>& fft_twiddles(size_t n, Fe root) {
+    static thread_local std::map<std::pair<size_t, u128>, std::vector<Fe>> cache;
+    auto key = std::make_pair(n, root.v);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
     std::vector<Fe> tw(n / 2 ? n / 2 : 1);
     tw[0] = FE_ONE;
     for (size_t i = 1; i < n / 2; i++) tw[i] = mul(tw[i - 1], root);
+    return cache.emplace(key, std::move(tw)).first->second;
+}
+static inline void fft_in_place(Fe* a, size_t n, Fe root) {
+    // iterative radix-2 DIT, natural in / natural out
+    for (size_t i = 1, j = 0; i < n; i++) {  // bit-reversal permutation
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    const std::vector<Fe>& tw = fft_twiddles(n, root);
     for (size_t len = 2; len <= n; len <<= 1) {
         size_t half = len / 2, step = n / len;
         for (size_t s = 0; s < n; s += len)
