@@ -39,14 +39,15 @@ struct LdeMat {
     uint32_t log_n, log_beta, w, log_p;   // log_p: slots per stored chunk (P' = P >> log_shard)
     uint32_t log_shard, bw, log_bw, view, q_self;
     uint64_t blk_stride;                  // elements between column blocks (recv view): panels * bw * P'
+    uint32_t k0, log_kc;                  // cosets stored: k in [k0, k0 + 2^log_kc) (all of them: k0 = 0, log_kc = log_beta)
 };
 __device__ __forceinline__ uint32_t lde_full_log_p(const LdeMat& m) { return m.log_p + m.log_shard; }
 // address of (row (k, i), column 0 of block 0)
 __device__ __forceinline__ size_t lde_row_base(const LdeMat& m, uint32_t k, uint32_t i) {
     const uint32_t lt = m.log_n - lde_full_log_p(m);
     const uint32_t t_low = i & ((1u << lt) - 1u), slot = i >> lt;
-    const size_t panel = ((size_t)k << lt) + t_low;
-    const size_t np = (size_t)1 << (m.log_beta + lt);
+    const size_t panel = ((size_t)(k - m.k0) << lt) + t_low;
+    const size_t np = (size_t)1 << (m.log_kc + lt);
     const uint32_t chunk = m.view == 0 ? (slot >> m.log_p) : 0u;
     return (((size_t)chunk * np + panel) * m.bw << m.log_p) + (slot & ((1u << m.log_p) - 1u));
 }
@@ -100,6 +101,7 @@ struct NttPass {
     uint32_t log_lde;              // log2(n * beta) for coset transforms
     uint32_t out_panel;            // final pass of an LDE: write the panel layout
     uint32_t log_shard;            // panel layout split into 2^log_shard slot chunks (multi-GPU send view)
+    uint32_t panel_k0, log_kc;     // the output stores cosets [panel_k0, panel_k0 + 2^log_kc) only (coset-sharded LDEs)
     uint32_t do_scale;             // multiply outputs by `scale` (1/n for interpolation)
     fe scale;
     PowTab roots;                  // w_{2^log_tab}^e
@@ -210,9 +212,9 @@ __global__ void __launch_bounds__(256, 3) k_ntt_pass(const NttPass p) {
     // store
     if (p.out_panel) {
         // panel = k*2^a + t_low, slot = t_high; consecutive threads write consecutive slots of one column
-        const size_t panel = ((size_t)k << p.a) + t_low;
+        const size_t panel = ((size_t)(k - p.panel_k0) << p.a) + t_low;
         const uint32_t lp = logS - p.log_shard;                       // slots per stored chunk
-        const size_t np = (size_t)1 << (p.log_lde - p.log_n + p.a);   // panels = beta * 2^a
+        const size_t np = (size_t)1 << (p.log_kc + p.a);              // panels = stored cosets * 2^a
         for (uint32_t idx = threadIdx.x; idx < E; idx += blockDim.x) {
             const uint32_t jj = idx >> logS, th = idx & (S - 1u);
             if (c_base + jj < p.ncols) {
@@ -248,23 +250,39 @@ __global__ void k_scale_pow(fe* x, uint64_t n, PowTab base, fe scale) {
 // one thread per stored LDE row, enumerated (panel, slot) so that a warp reads 32 consecutive slots per column.
 // leaves: digest array indexed by (global leaf index - leaf0); in the multi-GPU recv view a rank stores and hashes only
 // the rows of its slot chunk, which are the contiguous leaves [q N/G, (q+1) N/G).
-__global__ void __launch_bounds__(128) k_hash_lde_rows(const LdeMat m, uint32_t* __restrict__ leaves, uint64_t leaf0) {
+__global__ void __launch_bounds__(128) k_hash_lde_rows(const LdeMat m, uint32_t* __restrict__ leaves, uint64_t leaf0, uint32_t compact) {
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lpf = lde_full_log_p(m), lt = m.log_n - lpf;
-    const uint32_t log_rows = m.log_beta + lt + (m.view == 0 ? lpf : m.log_p);   // rows stored on this rank
+    const uint32_t log_rows = m.log_kc + lt + (m.view == 0 ? lpf : m.log_p);   // rows stored on this rank
     if (gid >> log_rows) return;
     const uint32_t lslots = m.view == 0 ? lpf : m.log_p;
     const uint32_t s = (uint32_t)gid & ((1u << lslots) - 1u);
     const uint32_t panel = (uint32_t)(gid >> lslots);
     const uint32_t slot = m.view == 0 ? s : ((m.q_self << m.log_p) + s);
-    const uint32_t k = panel >> lt, t_low = panel & ((1u << lt) - 1u);
+    const uint32_t k = m.k0 + (panel >> lt), t_low = panel & ((1u << lt) - 1u);
     const uint32_t i = t_low + (slot << lt);
-    const uint64_t r = ((uint64_t)i << m.log_beta) + k;
+    // leaf index: global r = i*beta + k; compact (coset-sharded matrices): i * (stored cosets) + local coset
+    const uint64_t r = compact ? (((uint64_t)i << m.log_kc) + (k - m.k0)) : (((uint64_t)i << m.log_beta) + k - leaf0);
     uint32_t d[8];
     b3_hash_elems(m.data + lde_row_base(m, k, i), (size_t)1 << m.log_p, m.w, d, m.log_bw, m.blk_stride);
-    uint4* o = reinterpret_cast<uint4*>(leaves + (r - leaf0) * 8);
+    uint4* o = reinterpret_cast<uint4*>(leaves + r * 8);
     o[0] = make_uint4(d[0], d[1], d[2], d[3]);
     o[1] = make_uint4(d[4], d[5], d[6], d[7]);
+}
+// multi-GPU: after an all-gather of per-rank compact arrays [src][i * kc + kl] (kc = stored cosets per rank), put item
+// (i, k = src*kc + kl) at natural LDE position i*beta + k.  `words` 32-bit words per item (8: digests, 4: field elements).
+__global__ void k_permute_coset_items(const uint32_t* __restrict__ gathered, uint32_t* __restrict__ out, uint32_t log_n, uint32_t log_beta,
+                                      uint32_t log_kc, uint32_t words) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (item, 16-byte quarter)
+    const uint32_t q4 = words >> 2;
+    const uint64_t item = t / q4;
+    if (item >> (log_n + log_beta)) return;
+    const uint32_t part = (uint32_t)(t - item * q4);
+    const uint32_t k = (uint32_t)item & ((1u << log_beta) - 1u);
+    const uint64_t i = item >> log_beta;
+    const uint32_t src = k >> log_kc, kl = k & ((1u << log_kc) - 1u);
+    const uint64_t from = ((uint64_t)src << (log_n + log_kc)) + (i << log_kc) + kl;
+    reinterpret_cast<uint4*>(out)[item * q4 + part] = reinterpret_cast<const uint4*>(gathered)[from * q4 + part];
 }
 
 // FRI layer rows: leaf_i = hash_elements([e[i + j*rows]]_{j<F})   (winter-fri build_layer / transpose_slice)
@@ -487,10 +505,11 @@ __global__ void __launch_bounds__(256) k_deep_combine(const fe* __restrict__ pol
 }
 // k_deep_eval: each thread handles RPT rows (one Montgomery batch inversion per thread)
 #define ZKB_DEEP_RPT 8
+// compact = 1 (coset-sharded AB matrix): out index = i * (stored cosets) + local coset, else the natural position i*beta + k
 __global__ void __launch_bounds__(128) k_deep_eval(const LdeMat m, fe z, fe zg, fe az, fe abz, fe azg, PowTab roots, uint32_t log_tab,
-                                                   fe* __restrict__ out) {
+                                                   fe* __restrict__ out, uint32_t compact) {
     const uint32_t log_N = m.log_n + m.log_beta;
-    const uint64_t N = (uint64_t)1 << log_N;
+    const uint64_t N = (uint64_t)1 << (m.log_n + m.log_kc);   // rows stored
     const uint64_t nthreads = N / ZKB_DEEP_RPT;
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= nthreads) return;
@@ -503,10 +522,10 @@ __global__ void __launch_bounds__(128) k_deep_eval(const LdeMat m, fe z, fe zg, 
         const uint64_t gid = tid + (uint64_t)s * nthreads;
         const uint32_t slot = (uint32_t)gid & ((1u << m.log_p) - 1u);
         const uint32_t panel = (uint32_t)(gid >> m.log_p);
-        const uint32_t k = panel >> lt, t_low = panel & ((1u << lt) - 1u);
+        const uint32_t k = m.k0 + (panel >> lt), t_low = panel & ((1u << lt) - 1u);
         const uint32_t i = t_low + (slot << lt);
         const uint32_t r = (i << m.log_beta) + k;
-        rr[s] = r;
+        rr[s] = compact ? ((i << m.log_kc) + (k - m.k0)) : r;
         const fe* row = m.data + (((size_t)panel * 2) << m.log_p) + slot;
         fe a = fe_load(row), ab = fe_load(row + ((size_t)1 << m.log_p));
         fe x = powtab(roots, r << (log_tab - log_N));
@@ -601,6 +620,7 @@ __global__ void k_gather_lde_rows(const LdeMat m, const uint32_t* __restrict__ p
     const uint32_t q = idx / m.w, j = idx - q * m.w;
     const uint32_t r = __ldg(pos + q);
     const uint32_t k = r & ((1u << m.log_beta) - 1u), i = r >> m.log_beta;
+    if (k - m.k0 >= (1u << m.log_kc)) { fe_store(out + idx, fe_zero()); return; }   // coset held by another rank
     fe_store(out + idx, fe_load(m.data + lde_addr(m, k, i, j)));
 }
 // FriProver::build_proof / query_layer: rows [e[p + j*rows]]_{j<16}

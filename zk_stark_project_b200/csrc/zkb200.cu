@@ -138,20 +138,28 @@ struct zkb_ctx {
 
     // ==========================================================================================================
     void count() { launches++; }
-    LdeMat std_mat(fe* data, uint32_t w, uint32_t log_p) const { return LdeMat{data, log_n, log_beta, w, log_p, 0, w, 31, 0, 0, 0}; }
+    LdeMat std_mat(fe* data, uint32_t w, uint32_t log_p) const { return LdeMat{data, log_n, log_beta, w, log_p, 0, w, 31, 0, 0, 0, 0, log_beta}; }
+    // coset-sharded matrices of a multi-GPU proof (composition columns, DEEP pair): rank r stores cosets [r*kc, (r+1)*kc)
+    bool mg_coset() const { return mg_active && (uint32_t)mg_world <= air.blowup; }
+    uint32_t mg_log_kc() const { return log_beta - log_g; }
+    LdeMat coset_mat(fe* data, uint32_t w, uint32_t log_p) const {
+        LdeMat m = std_mat(data, w, log_p);
+        if (mg_coset()) { m.log_kc = mg_log_kc(); m.k0 = (uint32_t)mg_rank << m.log_kc; }
+        return m;
+    }
     // single GPU: the whole trace LDE; multi-GPU: the send view (this rank's columns, all rows)
     LdeMat lde_mat() const {
         if (!mg_active) return std_mat(d_lde.as<fe>(), air.w, lde_log_p);
-        return LdeMat{d_lde.as<fe>(), log_n, log_beta, air.w >> log_g, lde_log_p - log_g, log_g, air.w >> log_g, 31, 0, (uint32_t)mg_rank, 0};
+        return LdeMat{d_lde.as<fe>(), log_n, log_beta, air.w >> log_g, lde_log_p - log_g, log_g, air.w >> log_g, 31, 0, (uint32_t)mg_rank, 0, 0, log_beta};
     }
     // multi-GPU recv view: all columns, this rank's rows
     LdeMat lde_rows_mat() const {
         const uint32_t wl = air.w >> log_g, lp = lde_log_p - log_g;
         const uint64_t np = (uint64_t)1 << (log_beta + log_n - lde_log_p);
-        return LdeMat{d_lde_rows.as<fe>(), log_n, log_beta, air.w, lp, log_g, wl, log2u(wl), 1, (uint32_t)mg_rank, (np * wl) << lp};
+        return LdeMat{d_lde_rows.as<fe>(), log_n, log_beta, air.w, lp, log_g, wl, log2u(wl), 1, (uint32_t)mg_rank, (np * wl) << lp, 0, log_beta};
     }
-    LdeMat comp_mat() const { return std_mat(d_comp_lde.as<fe>(), c, comp_log_p); }
-    LdeMat ab_mat() const { return std_mat(d_ab_lde.as<fe>(), 2, ab_log_p); }
+    LdeMat comp_mat() const { return coset_mat(d_comp_lde.as<fe>(), c, comp_log_p); }
+    LdeMat ab_mat() const { return coset_mat(d_ab_lde.as<fe>(), 2, ab_log_p); }
 
     void init(int dev, void* strm) {
         int ndev = 0;
@@ -259,6 +267,7 @@ struct zkb_ctx {
         uint32_t log_lde;  // coset LDE only
         bool scale; HF scale_by;
         uint32_t log_shard = 0;  // coset LDE only: split every panel into 2^log_shard slot chunks (multi-GPU send view)
+        uint32_t coset_lo = 0, coset_cnt = 0;  // coset LDE only: evaluate cosets [lo, lo + cnt) (0 = all) into a buffer holding just those
     };
     // returns log_p of the panel layout for LDEs (size of the last pass)
     uint32_t run_xform(const Xform& x, DevBuf& s1, DevBuf& s2) {
@@ -266,7 +275,8 @@ struct zkb_ctx {
         std::vector<uint32_t> bnd = plan_layers(x.log_len, cj);
         const uint32_t passes = (uint32_t)bnd.size();
         const uint64_t len = (uint64_t)1 << x.log_len;
-        const uint32_t n_cosets = x.coset_lde ? (1u << (x.log_lde - x.log_len)) : 1;
+        const uint32_t all_cosets = x.coset_lde ? (1u << (x.log_lde - x.log_len)) : 1;
+        const uint32_t n_cosets = (x.coset_lde && x.coset_cnt) ? x.coset_cnt : all_cosets;
         // coset batches bound the scratch size
         uint32_t batch = n_cosets;
         if (passes > 1) {
@@ -285,7 +295,8 @@ struct zkb_ctx {
                 const bool last = (q + 1 == passes);
                 p.in = src; p.w_in = w_src; p.col0_in = c0_src; p.in_coset_stride = src_stride;
                 p.log_n = x.log_len; p.a = a; p.b = bnd[q];
-                p.ncols = x.ncols; p.cj = cj; p.n_cosets = nk; p.coset0 = k0;
+                p.ncols = x.ncols; p.cj = cj; p.n_cosets = nk; p.coset0 = x.coset_lo + k0;
+                p.panel_k0 = x.coset_lo; p.log_kc = log2u(n_cosets);
                 p.coset = x.coset_lde ? 1 : 0; p.inverse = x.inverse ? 1 : 0;
                 p.log_tab = log_tab; p.log_lde = x.coset_lde ? x.log_lde : 0;
                 p.roots = roots; p.pow3 = d_pow3.as<fe>();
@@ -396,7 +407,7 @@ struct zkb_ctx {
         }
         CK(cudaEventRecord(ev[3], stream));
         // K3: leaves
-        k_hash_lde_rows<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(lde_mat(), d_tree.as<uint32_t>() + N * 8, 0);
+        k_hash_lde_rows<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(lde_mat(), d_tree.as<uint32_t>() + N * 8, 0, 0);
         check_launch();
         CK(cudaEventRecord(ev[4], stream));
         // K4: tree
@@ -486,7 +497,7 @@ struct zkb_ctx {
         // K3/K4 on this rank's rows
         const uint64_t Nl = N / G;
         d_tree.ensure(2 * Nl * 32);
-        k_hash_lde_rows<<<(unsigned)((Nl + 127) / 128), 128, 0, stream>>>(lde_rows_mat(), d_tree.as<uint32_t>() + Nl * 8, (uint64_t)mg_rank * Nl);
+        k_hash_lde_rows<<<(unsigned)((Nl + 127) / 128), 128, 0, stream>>>(lde_rows_mat(), d_tree.as<uint32_t>() + Nl * 8, (uint64_t)mg_rank * Nl, 0);
         check_launch();
         CK(cudaEventRecord(ev[4], stream));
         build_merkle(d_tree.as<uint32_t>(), Nl);
@@ -634,13 +645,23 @@ struct zkb_ctx {
             constraints_eval_window(alpha, lde_mat(), 0, air.w, d_comp_evals.as<fe>());
         } else {
             // column-sharded: partial evaluation over this rank's columns, all-gather, field sum
-            const uint32_t wl = air.w >> log_g;
-            d_mg_a.ensure(n * ce * 16);
-            d_mg_b.ensure(n * ce * 16 * mg_world);
+            // reduce-scatter by hand (NCCL cannot add mod p): slice q of every rank's partial vector goes to rank q, which
+            // sums the G slices; the summed slices are all-gathered
+            const uint32_t wl = air.w >> log_g, G = (uint32_t)mg_world;
+            const uint64_t total = n * ce, sl = total / G;
+            d_mg_a.ensure(total * 16);
+            d_mg_b.ensure(total * 16 + sl * 16);
             constraints_eval_window(alpha, lde_mat(), mg_rank * wl, wl, d_mg_a.as<fe>());
-            NK(g_nccl.AllGather(d_mg_a.p, d_mg_b.p, n * ce * 16, ncclUint8, comm, stream));
-            k_sum_partials<<<(unsigned)((n * ce + 255) / 256), 256, 0, stream>>>(d_mg_b.as<fe>(), mg_world, n * ce, n * ce, d_comp_evals.as<fe>());
+            NK(g_nccl.GroupStart());
+            for (uint32_t q = 0; q < G; q++) {
+                NK(g_nccl.Send(d_mg_a.as<fe>() + q * sl, sl * 16, ncclUint8, (int)q, comm, stream));
+                NK(g_nccl.Recv(d_mg_b.as<fe>() + q * sl, sl * 16, ncclUint8, (int)q, comm, stream));
+            }
+            NK(g_nccl.GroupEnd());
+            fe* mine = d_mg_b.as<fe>() + total;
+            k_sum_partials<<<(unsigned)((sl + 255) / 256), 256, 0, stream>>>(d_mg_b.as<fe>(), G, sl, sl, mine);
             check_launch();
+            NK(g_nccl.AllGather(mine, d_comp_evals.p, sl * 16, ncclUint8, comm, stream));
         }
         CK(cudaEventRecord(ev[1], stream));
         if (evals_out) d2h(evals_out, d_comp_evals.p, n * ce * 16);
@@ -667,13 +688,29 @@ struct zkb_ctx {
         // evaluate the c column polynomials over the LDE domain (panel layout, width c)
         d_comp_lde.ensure(N * c * 16);
         // (measured: c single-column transforms with 4096-point tiles beat one 8-wide batch, which needs a third pass)
+        // multi-GPU: every rank extends the columns over its own beta/G cosets only, hashes those rows, and the leaf digests
+        // are all-gathered and put in leaf order; the (small) tree is then built by every rank
+        const bool cs = mg_coset();
+        const uint32_t kc = cs ? (1u << mg_log_kc()) : (uint32_t)air.blowup;
+        const uint64_t Nloc = n * kc;
         for (uint32_t i = 0; i < c; i++) {
             Xform x{coef + (size_t)i * n, 1, 0, d_comp_lde.as<fe>(), c, i, 1, log_n, false, true, log_N, false, HF()};
+            if (cs) { x.coset_lo = (uint32_t)mg_rank * kc; x.coset_cnt = kc; }
             comp_log_p = run_xform(x, d_tmp1, d_tmp2);
         }
         d_comp_tree.ensure(2 * N * 32);
-        k_hash_lde_rows<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(comp_mat(), d_comp_tree.as<uint32_t>() + N * 8, 0);
-        check_launch();
+        if (!cs) {
+            k_hash_lde_rows<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(comp_mat(), d_comp_tree.as<uint32_t>() + N * 8, 0, 0);
+            check_launch();
+        } else {
+            d_mg_a.ensure(Nloc * 32); d_mg_b.ensure(N * 32);
+            k_hash_lde_rows<<<(unsigned)((Nloc + 127) / 128), 128, 0, stream>>>(comp_mat(), d_mg_a.as<uint32_t>(), 0, 1);
+            check_launch();
+            NK(g_nccl.AllGather(d_mg_a.p, d_mg_b.p, Nloc * 32, ncclUint8, comm, stream));
+            k_permute_coset_items<<<(unsigned)((N * 2 + 255) / 256), 256, 0, stream>>>(d_mg_b.as<uint32_t>(), d_comp_tree.as<uint32_t>() + N * 8, log_n,
+                                                                                   log_beta, mg_log_kc(), 8);
+            check_launch();
+        }
         build_merkle(d_comp_tree.as<uint32_t>(), N);
         CK(cudaEventRecord(ev[1], stream));
         Digest32 root;
@@ -776,15 +813,31 @@ struct zkb_ctx {
         }
         CK(cudaStreamSynchronize(stream));  // `g` must outlive the copy
         d_ab_lde.ensure(N * 2 * 16);
-        {
+        d_deep.ensure(N * 16);
+        if (!mg_coset()) {
             Xform x{d_ab.as<fe>(), 2, 0, d_ab_lde.as<fe>(), 2, 0, 2, log_n, false, true, log_N, false, HF()};
             ab_log_p = run_xform(x, d_tmp1, d_tmp2);
+            const uint64_t threads = N / ZKB_DEEP_RPT;
+            k_deep_eval<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(ab_mat(), to_fe(z), to_fe(zg), to_fe(az), to_fe(az + bz), to_fe(azg),
+                                                                              roots, log_tab, d_deep.as<fe>(), 0);
+            check_launch();
+        } else {
+            // multi-GPU: extend and evaluate on this rank's cosets, all-gather the evaluations, restore natural order
+            const uint32_t kc = 1u << mg_log_kc();
+            const uint64_t Nloc = n * kc;
+            Xform x{d_ab.as<fe>(), 2, 0, d_ab_lde.as<fe>(), 2, 0, 2, log_n, false, true, log_N, false, HF()};
+            x.coset_lo = (uint32_t)mg_rank * kc; x.coset_cnt = kc;
+            ab_log_p = run_xform(x, d_tmp1, d_tmp2);
+            d_mg_a.ensure(Nloc * 16); d_mg_b.ensure(N * 16);
+            const uint64_t threads = Nloc / ZKB_DEEP_RPT;
+            k_deep_eval<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(ab_mat(), to_fe(z), to_fe(zg), to_fe(az), to_fe(az + bz), to_fe(azg),
+                                                                              roots, log_tab, d_mg_a.as<fe>(), 1);
+            check_launch();
+            NK(g_nccl.AllGather(d_mg_a.p, d_mg_b.p, Nloc * 16, ncclUint8, comm, stream));
+            k_permute_coset_items<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(d_mg_b.as<uint32_t>(), d_deep.as<uint32_t>(), log_n, log_beta,
+                                                                               mg_log_kc(), 4);
+            check_launch();
         }
-        d_deep.ensure(N * 16);
-        const uint64_t threads = N / ZKB_DEEP_RPT;
-        k_deep_eval<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(ab_mat(), to_fe(z), to_fe(zg), to_fe(az), to_fe(az + bz), to_fe(azg),
-                                                                          roots, log_tab, d_deep.as<fe>());
-        check_launch();
         CK(cudaEventRecord(ev[1], stream));
         CK(cudaEventSynchronize(ev[1]));
         CK(cudaEventElapsedTime(&times.deep, ev[0], ev[1]));
@@ -911,6 +964,18 @@ struct zkb_ctx {
         std::vector<uint8_t> host((size_t)np * width * 16 + flat.size() * 32);
         d2h(host.data(), base + o_rows, host.size());  // rows and digests are adjacent
         rows.assign(host.begin(), host.begin() + (size_t)np * width * 16);
+        if (which == 1 && mg_coset()) {
+            // coset-sharded composition LDE: a queried row lives on the rank that owns its coset (the tree is replicated)
+            const size_t rb = (((size_t)np * width * 16 + 15) / 16) * 16;
+            d_mg_b.ensure(rb * mg_world);
+            NK(g_nccl.AllGather(base + o_rows, d_mg_b.p, rb, ncclUint8, comm, stream));
+            std::vector<uint8_t> all(rb * mg_world);
+            d2h(all.data(), d_mg_b.p, all.size());
+            for (uint32_t q = 0; q < np; q++) {
+                const size_t own = (pos[q] & (air.blowup - 1)) >> mg_log_kc();
+                memcpy(&rows[(size_t)q * width * 16], &all[own * rb + (size_t)q * width * 16], (size_t)width * 16);
+            }
+        }
         paths = batch_proof_bytes(depth, plan, host.data() + (size_t)np * width * 16);
     }
 
