@@ -380,7 +380,8 @@ def main():
                                "frac": (alg["total"] / peak / 1e6) / (ms_latency / args.steps)},
             "stages": per_stage,
             "e2e": {"value": proofs_per_step * args.steps / (ms_e2e * 1e-3), "unit": "proofs/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": nbytes * (world if sharded else 1), "d2h_bytes_per_step": len(proof)},
+                    "h2d_bytes_per_step": nbytes * (world if sharded else world * inflight),
+                    "d2h_bytes_per_step": len(proof) * (1 if sharded else world * inflight)},
             "gpu_launches": launches,
             "clocks": sampler.summary(t_wall0, t_wall1),
         }

@@ -163,6 +163,15 @@ int32_t zkb_mimc_trace(zkb_ctx* ctx, const uint8_t* seeds, uint32_t w, uint64_t 
 /* same, leaving the trace in device memory; returns the device pointer (owned by the context) */
 int32_t zkb_mimc_trace_device(zkb_ctx* ctx, const uint8_t* seeds, uint32_t w, uint64_t n, const uint8_t* round_constants,
                               uint32_t n_rc, void** d_out);
+/* host-side BLAKE3-256 (Blake3_256::hash); no device needed — used by the CPU verifier of the Python mirror */
+int32_t zkb_blake3_host(const uint8_t* data, uint64_t len, uint8_t out[32]);
+/* batched mimc_cipher (src/helper.rs:213-220): out[i] = mimc_cipher(inputs[i], round_constants[i], zs[i]); benches/bench_mimc.rs:17-34 */
+int32_t zkb_mimc_cipher_batch(zkb_ctx* ctx, const uint8_t* inputs, const uint8_t* round_constants, const uint8_t* zs, uint64_t count,
+                              uint8_t* out);
+/* batched mimc_hash_matrix (src/helper.rs:222-233; the aggregation digest, src/aggregation/prover.rs:176-178):
+ * w = count matrices [ac][fe], b = count vectors [ac]; benches/bench_mimc.rs:39-57 */
+int32_t zkb_mimc_hash_matrix_batch(zkb_ctx* ctx, const uint8_t* w, const uint8_t* b, uint32_t ac, uint32_t fe, const uint8_t* round_constants,
+                                   uint32_t n_rc, uint64_t count, uint8_t* out);
 /* upload a column-major host trace into a context-owned device buffer (for device-resident timing) */
 int32_t zkb_upload_trace(zkb_ctx* ctx, const uint8_t* const* cols, uint32_t w, uint64_t n, void** d_out);
 

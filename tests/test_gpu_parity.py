@@ -83,6 +83,7 @@ def _prove_both(gpu_ctx, oracle, air, trace):
     assert diff is None, f"transcripts diverge at `{diff}`"
     assert proof_g == proof_o, "proof bytes differ although the transcript matches"
     oracle.verify(air, proof_g)
+    assert Z.verify(proof_g, air)  # the product's own (Python) verifier
     return proof_g
 
 
@@ -267,3 +268,18 @@ def test_pageable_and_scattered_columns(gpu_ctx, oracle):
     gpu_ctx.lib.zkb_free(out)
     ref, _, _ = oracle.prove(air, trace.to_bytes())
     assert proof == ref
+
+
+def test_mimc_helpers_batch(gpu_ctx):
+    """GPU mimc_cipher / mimc_hash_matrix against the Python restatement of src/helper.rs:213-233 (benches/bench_mimc.rs shapes)."""
+    rng = random.Random(5)
+    xs = [rng.randrange(P) for _ in range(300)] + [0, P - 1]
+    rcs = [rng.randrange(2**64) for _ in xs]
+    zs = [0] * 100 + [rng.randrange(P) for _ in range(len(xs) - 100)]
+    assert L.mimc_cipher_batch(gpu_ctx, xs, rcs, zs) == [Z.mimc_cipher(x, r, z) for x, r, z in zip(xs, rcs, zs)]
+    rc = Z.get_round_constants()
+    ws = [[[rng.randrange(P) for _ in range(9)] for _ in range(6)] for _ in range(40)]
+    bs = [[rng.randrange(P) for _ in range(6)] for _ in range(40)]
+    ws[0] = [[Z.f64_to_felt(42.0)] * 9 for _ in range(6)]  # the criterion bench's fixed input
+    bs[0] = [Z.f64_to_felt(1.0)] * 6
+    assert L.mimc_hash_matrix_batch(gpu_ctx, ws, bs, rc) == [Z.mimc_hash_matrix(w, b, rc) for w, b in zip(ws, bs)]

@@ -671,6 +671,35 @@ __global__ void k_mimc_trace(const fe* __restrict__ seeds, uint32_t w, uint64_t 
     }
 }
 
+// batched MiMC helpers of the reference: mimc_cipher (src/helper.rs:213-220) and mimc_hash_matrix (:222-233), one thread
+// per instance — the GPU counterpart of benches/bench_mimc.rs:17-57
+__device__ __forceinline__ fe mimc_cipher_dev(fe inp, const fe rc, const fe z) {
+    const fe k = fe_add(rc, z);
+    for (int r = 0; r < 64; r++) {
+        fe a1 = fe_add(inp, k);
+        fe a2 = fe_sqr(a1), a4 = fe_sqr(a2), a6 = fe_mul(a4, a2);
+        inp = fe_mul(a6, a1);
+    }
+    return fe_add(inp, z);
+}
+__global__ void k_mimc_cipher_batch(const fe* __restrict__ x, const fe* __restrict__ rc, const fe* __restrict__ z, uint64_t n, fe* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe_store(out + i, mimc_cipher_dev(fe_load(x + i), fe_load(rc + i), fe_load(z + i)));
+}
+// w: [count][ac][fe], b: [count][ac]
+__global__ void k_mimc_hash_matrix_batch(const fe* __restrict__ w, const fe* __restrict__ b, uint32_t ac, uint32_t fe_n, const fe* __restrict__ rc,
+                                         uint32_t n_rc, uint64_t count, fe* __restrict__ out) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    fe z = fe_zero();
+    for (uint32_t i = 0; i < ac; i++) {
+        for (uint32_t j = 0; j < fe_n; j++) z = mimc_cipher_dev(fe_load(w + (t * ac + i) * fe_n + j), fe_ldg(rc + j % n_rc), z);
+        z = mimc_cipher_dev(fe_load(b + t * ac + i), fe_ldg(rc + i % n_rc), z);
+    }
+    fe_store(out + t, z);
+}
+
 // elementwise kernels used by tests (KATs of the device field / hash against the oracle)
 __global__ void k_test_field(const fe* a, const fe* b, fe* mul, fe* add, fe* sub, fe* inv, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

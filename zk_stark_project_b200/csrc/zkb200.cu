@@ -237,6 +237,8 @@ struct zkb_ctx {
     }
 
     // ---- NTT planning ---------------------------------------------------------------------------------------
+    // 16-column tiles (256 rows, 3 blocks/SM) were measured against 8-column tiles at 4 blocks/SM (64 registers): no gain,
+    // the pass kernel is bound by integer issue, not occupancy
     static uint32_t pick_cj(uint32_t ncols) { return ncols >= 9 ? 16 : ncols >= 5 ? 8 : ncols >= 3 ? 4 : ncols == 2 ? 2 : 1; }
     static std::vector<uint32_t> plan_layers(uint32_t log_len, uint32_t cj) {
         uint32_t maxlog = 12 - log2u(cj);  // S * cj <= 4096 elements in shared memory
@@ -1244,6 +1246,42 @@ int32_t zkb_mimc_trace(zkb_ctx* ctx, const uint8_t* seeds, uint32_t w, uint64_t 
     int32_t r = zkb_mimc_trace_device(ctx, seeds, w, n, rc, n_rc, &d);
     if (r != ZKB_OK) return r;
     return guarded(ctx, [&] { if (!out) throw InvalidArg("null output"); ctx->d2h(out, d, (size_t)w * n * 16); });
+}
+// host-side BLAKE3 (the channel's hash) for callers that verify proofs on the CPU; needs no device
+int32_t zkb_blake3_host(const uint8_t* data, uint64_t len, uint8_t out[32]) {
+    if ((!data && len) || !out) { g_last_error = "null argument"; return ZKB_ERR_INVALID; }
+    b3_hash_host(data, len, out);
+    return ZKB_OK;
+}
+int32_t zkb_mimc_cipher_batch(zkb_ctx* ctx, const uint8_t* inputs, const uint8_t* round_constants, const uint8_t* zs, uint64_t count, uint8_t* out) {
+    return guarded(ctx, [&] {
+        if (!inputs || !round_constants || !zs || !out) throw InvalidArg("null argument");
+        if (count == 0) return;
+        CK(cudaSetDevice(ctx->device));
+        ctx->d_aux.ensure(count * 16 * 4);
+        fe* b = ctx->d_aux.as<fe>();
+        ctx->h2d(b, inputs, count * 16); ctx->h2d(b + count, round_constants, count * 16); ctx->h2d(b + 2 * count, zs, count * 16);
+        k_mimc_cipher_batch<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(b, b + count, b + 2 * count, count, b + 3 * count);
+        ctx->check_launch();
+        ctx->d2h(out, b + 3 * count, count * 16);
+    });
+}
+int32_t zkb_mimc_hash_matrix_batch(zkb_ctx* ctx, const uint8_t* w, const uint8_t* b, uint32_t ac, uint32_t fe_, const uint8_t* round_constants,
+                                   uint32_t n_rc, uint64_t count, uint8_t* out) {
+    return guarded(ctx, [&] {
+        if (!w || !b || !round_constants || !out || ac == 0 || fe_ == 0 || n_rc == 0) throw InvalidArg("bad mimc_hash_matrix request");
+        if (count == 0) return;
+        CK(cudaSetDevice(ctx->device));
+        const size_t per = (size_t)ac * fe_ + ac;
+        ctx->d_aux.ensure((count * per + n_rc + count) * 16);
+        fe* base = ctx->d_aux.as<fe>();
+        ctx->h2d(base, w, count * ac * fe_ * 16); ctx->h2d(base + count * ac * fe_, b, count * ac * 16);
+        ctx->h2d(base + count * per, round_constants, (size_t)n_rc * 16);
+        k_mimc_hash_matrix_batch<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(base, base + count * ac * fe_, ac, fe_, base + count * per, n_rc,
+                                                                                          count, base + count * per + n_rc);
+        ctx->check_launch();
+        ctx->d2h(out, base + count * per + n_rc, count * 16);
+    });
 }
 int32_t zkb_upload_trace(zkb_ctx* ctx, const uint8_t* const* cols, uint32_t w, uint64_t n, void** d_out) {
     return guarded(ctx, [&] {

@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libzkb200.so")
+LIB_PATH = os.environ.get("ZKB_LIB", os.path.join(HERE, "libzkb200.so"))
 _lib = None
 
 
@@ -77,7 +77,7 @@ EXPORTS = [
     "zkb_host_free", "zkb_prove", "zkb_prove_device", "zkb_free", "zkb_begin", "zkb_trace_commit", "zkb_trace_commit_device",
     "zkb_trace_read_frame", "zkb_trace_polys_read", "zkb_constraints_eval", "zkb_constraints_commit", "zkb_ood_eval",
     "zkb_deep_compose", "zkb_fri_num_layers", "zkb_fri_commit_layer", "zkb_fri_fold", "zkb_fri_remainder", "zkb_grind",
-    "zkb_query", "zkb_mg_unique_id", "zkb_mg_init", "zkb_mg_prove", "zkb_mg_prove_device", "zkb_mimc_trace", "zkb_mimc_trace_device", "zkb_upload_trace", "zkb_test_field", "zkb_test_hash_elements",
+    "zkb_query", "zkb_mg_unique_id", "zkb_mg_init", "zkb_mg_prove", "zkb_mg_prove_device", "zkb_mimc_trace", "zkb_mimc_trace_device", "zkb_blake3_host", "zkb_mimc_cipher_batch", "zkb_mimc_hash_matrix_batch", "zkb_upload_trace", "zkb_test_field", "zkb_test_hash_elements",
     "zkb_test_merkle_root", "zkb_test_lde",
 ]
 
@@ -223,6 +223,37 @@ class Context:
         out = C.create_string_buffer(16 * n * w)
         self.check(self.lib.zkb_mimc_trace(self.handle, sb, C.c_uint32(w), C.c_uint64(n), rb, C.c_uint32(len(rc)), out))
         return out.raw
+
+
+def blake3_host(data):
+    """BLAKE3-256 on the host through the library (no device needed)."""
+    out = C.create_string_buffer(32)
+    rc = load().zkb_blake3_host(bytes(data), C.c_uint64(len(data)), out)
+    if rc != 0:
+        raise ZkbError(rc, "zkb_blake3_host failed")
+    return out.raw
+
+
+def mimc_cipher_batch(ctx, xs, rcs, zs):
+    """GPU `mimc_cipher` over a batch (src/helper.rs:213-220)."""
+    n = len(xs)
+    out = C.create_string_buffer(16 * max(n, 1))
+    pack = lambda v: b"".join(fe_bytes(x) for x in v)
+    ctx.check(ctx.lib.zkb_mimc_cipher_batch(ctx.handle, pack(xs), pack(rcs), pack(zs), C.c_uint64(n), out))
+    return [fe_int(out.raw[16 * i:16 * i + 16]) for i in range(n)]
+
+
+def mimc_hash_matrix_batch(ctx, ws, bs, round_constants):
+    """GPU `mimc_hash_matrix` over a batch of (w[ac][fe], b[ac]) pairs (src/helper.rs:222-233)."""
+    n = len(ws)
+    ac, fe_n = len(bs[0]), len(ws[0][0])
+    wb = b"".join(fe_bytes(x) for w in ws for row in w for x in row)
+    bb = b"".join(fe_bytes(x) for b in bs for x in b)
+    rb = b"".join(fe_bytes(x) for x in round_constants)
+    out = C.create_string_buffer(16 * n)
+    ctx.check(ctx.lib.zkb_mimc_hash_matrix_batch(ctx.handle, wb, bb, C.c_uint32(ac), C.c_uint32(fe_n), rb, C.c_uint32(len(round_constants)),
+                                                 C.c_uint64(n), out))
+    return [fe_int(out.raw[16 * i:16 * i + 16]) for i in range(n)]
 
 
 class PinnedBuffer:
