@@ -133,7 +133,7 @@ struct zkb_ctx {
     int mg_rank = 0, mg_world = 1;
     uint32_t log_g = 0;
     bool mg_active = false;             // the proof in flight is sharded
-    DevBuf d_lde_rows, d_mg_a, d_mg_b, d_comp_rm;  // recv view of the LDE; all-gather staging
+    DevBuf d_lde_rows, d_mg_a, d_mg_b;  // recv view of the LDE; all-gather staging
     std::vector<Digest32> mg_cap;       // heap of the replicated top log G levels: cap[1] = root, cap[G + q] = subtree root q
 
     // ==========================================================================================================
@@ -184,7 +184,7 @@ struct zkb_ctx {
         cudaStreamSynchronize(stream);
         for (DevBuf* b : {&d_trace, &d_bufA, &d_bufB, &d_tmp1, &d_tmp2, &d_lde, &d_tree, &d_small, &d_comp_evals, &d_comp_lde, &d_comp_tree,
                           &d_ab, &d_ab_lde, &d_deep, &d_roots_lo, &d_roots_hi, &d_inv3_lo, &d_inv3_hi, &d_pow3, &d_aux, &d_gather, &d_user_trace,
-                          &d_lde_rows, &d_mg_a, &d_mg_b, &d_comp_rm})
+                          &d_lde_rows, &d_mg_a, &d_mg_b})
             b->release();
         if (comm) { g_nccl.CommDestroy(comm); comm = nullptr; }
         for (auto& b : d_fri_evals) b.release();
