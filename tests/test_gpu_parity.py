@@ -283,3 +283,39 @@ def test_mimc_helpers_batch(gpu_ctx):
     ws[0] = [[Z.f64_to_felt(42.0)] * 9 for _ in range(6)]  # the criterion bench's fixed input
     bs[0] = [Z.f64_to_felt(1.0)] * 6
     assert L.mimc_hash_matrix_batch(gpu_ctx, ws, bs, rc) == [Z.mimc_hash_matrix(w, b, rc) for w, b in zip(ws, bs)]
+
+
+def test_full_size_training_proof(gpu_ctx, oracle):
+    """BASELINE.json configs[1] at full size (2^16 x 240, blowup 16, the reference's exact options: 40 queries, 21-bit grinding):
+    the CUDA proof equals the oracle's byte for byte and both verifier restatements accept it."""
+    n = 1 << 16
+    data = T.random_felts(240 * n, 0x5EED0002).reshape(240, n, 2)
+    air = T.synthetic_training_air(n, Z.ProofOptions.reference(), data)
+    proof, ts = gpu_ctx.prove_host(air, np.ascontiguousarray(data).ctypes.data)
+    assert ts.n_fri_layers == 4 and ts.n_positions <= 40
+    assert Z.verify(proof, air)
+    oracle.verify(air, proof)
+    ref, ts_o, _ = oracle.prove(air, data.tobytes())
+    assert T.transcript_diff(ts_o, ts) is None and proof == ref
+
+
+def test_large_mimc_proof_verifies(gpu_ctx, oracle):
+    """MiMC 64 x 2^18 (three NTT passes, LDE 2 GiB), trace generated on the device: size-independent acceptance check
+    (prove -> verify) with both verifiers, plus determinism of the proof."""
+    w, n = 64, 1 << 18
+    rc = Z.get_round_constants()
+    raw = gpu_ctx.mimc_trace([j + 1 for j in range(w)], n, rc)
+    data = np.frombuffer(raw, dtype=np.uint64).reshape(w, n, 2)
+    get = lambda c, r: int(data[c, r, 0]) | (int(data[c, r, 1]) << 64)
+    air = Z.MimcAir(w, n, Z.MimcInputs([get(j, 0) for j in range(w)], [get(j, n - 1) for j in range(w)]),
+                    Z.ProofOptions(40, 8, 21, Z.FieldExtension.NONE, 16, 7)).describe()
+    proof, ts = gpu_ctx.prove_host(air, np.ascontiguousarray(data).ctypes.data)
+    assert ts.n_fri_layers == 4
+    assert Z.verify(proof, air)
+    oracle.verify(air, proof)
+    again, _ = gpu_ctx.prove_host(air, np.ascontiguousarray(data).ctypes.data)
+    assert again == proof
+    # a wrong claimed result must be rejected
+    bad = dict(air, assertions=air["assertions"][:-1] + [(air["assertions"][-1][0], air["assertions"][-1][1], 12345)])
+    with pytest.raises(Z.VerifierError):
+        Z.verify(proof, bad)
