@@ -312,6 +312,29 @@ __global__ void __launch_bounds__(256) k_merkle_level(const uint32_t* __restrict
     o[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
 }
 
+// top of a Merkle heap in one launch: levels top, top/2, ..., 1 (top <= 512 nodes) by a single block; every level is
+// read back from global memory after a block barrier (the data is a few KB and stays in L1/L2)
+__global__ void __launch_bounds__(512) k_merkle_top(uint32_t* __restrict__ heap, uint32_t top) {
+    const uint32_t one_flags = B3_CHUNK_START | B3_CHUNK_END | B3_ROOT;
+    for (uint32_t lvl = top; lvl >= 1; lvl >>= 1) {
+        const uint32_t i = threadIdx.x;
+        if (i < lvl) {
+            const uint4* s = reinterpret_cast<const uint4*>(heap + (size_t)(2 * (lvl + i)) * 8);
+            uint32_t m[16], cv[8];
+            uint4 a = s[0], b = s[1], c = s[2], d = s[3];
+            m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+            m[8] = c.x; m[9] = c.y; m[10] = c.z; m[11] = c.w; m[12] = d.x; m[13] = d.y; m[14] = d.z; m[15] = d.w;
+            b3_iv(cv);
+            b3_compress(cv, m, 0, 64, one_flags);
+            uint4* o = reinterpret_cast<uint4*>(heap + (size_t)(lvl + i) * 8);
+            o[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+            o[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+        }
+        __threadfence_block();
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K5: DefaultConstraintEvaluator::evaluate (src/training/prover.rs:283-290) fused with
 // ConstraintEvaluationTable::combine: one thread per constraint-evaluation-domain point.

@@ -323,10 +323,13 @@ struct zkb_ctx {
 
     // ---- Merkle heap: heap[1] root, heap[N + l] leaves -----------------------------------------------------------
     void build_merkle(uint32_t* heap, uint64_t n_leaves) {
-        for (uint64_t lvl = n_leaves / 2; lvl >= 1; lvl >>= 1) {
+        uint64_t lvl = n_leaves / 2;
+        for (; lvl > 512; lvl >>= 1) {   // wide levels: one launch each
             k_merkle_level<<<(unsigned)((lvl + 255) / 256), 256, 0, stream>>>(heap + 2 * lvl * 8, heap + lvl * 8, lvl);
             check_launch();
         }
+        k_merkle_top<<<1, 512, 0, stream>>>(heap, (uint32_t)lvl);   // the last <= 10 levels in one launch
+        check_launch();
     }
 
     // ==========================================================================================================
