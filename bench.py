@@ -376,6 +376,12 @@ def main():
                          "algorithmic_bytes_per_proof": alg["lde"], "kernel_ms_per_proof": lde_ms,
                          "note": "bound by the FMA-heavy (IMAD) pipe, not HBM: a radix-2 f128 butterfly is ~105 SASS integer instructions "
                                  "per 32 bytes moved; ncu: sm__pipe_fmaheavy_cycles_active 73%, DRAM 9-16% (profiles/r1_ncu_ntt_lde_v1_radix8_regs.txt)"},
+            # what actually bounds K1/K2: integer issue.  Peak = register-resident radix-2 f128 butterflies/s measured on this pool's
+            # B200 by tools/mul_variants.cu (no memory traffic at all; profiles/r1_mul_variants_butterfly_peak.txt)
+            "compute_roofline": {"unit": "G butterflies/s", "peak": 203.5,
+                                 "achieved": (w_local * (n // 2) * (n.bit_length() - 1) * (beta + 1)) / (lde_ms * 1e-3) / 1e9,
+                                 "frac": (w_local * (n // 2) * (n.bit_length() - 1) * (beta + 1)) / (lde_ms * 1e-3) / 1e9 / 203.5,
+                                 "leaf_hash_alu_pipe_pct": 95.8, "source": "tools/mul_variants.cu, profiles/r1_ncu_hash_lde_rows.txt"},
             "proof_roofline": {"algorithmic_bytes": alg["total"], "t_hbm_ms": alg["total"] / peak / 1e6,
                                "frac": (alg["total"] / peak / 1e6) / (ms_latency / args.steps)},
             "stages": per_stage,
