@@ -34,6 +34,7 @@ WORKLOADS = {
     "training_2p20": ("training", 1 << 20, 240, 16, "training-shaped AIR, 2^20-row x 240-col trace, blowup 16 (LDE 60 GiB)"),
     "mimc_2p14": ("mimc", 1 << 14, 64, 8, "MiMC chains, 2^14 steps x 64 columns, blowup 8"),
     "mimc_2p20": ("mimc", 1 << 20, 64, 8, "MiMC chains, 2^20 steps x 64 columns, blowup 8 (LDE 8 GiB)"),
+    "mimc_2p22": ("mimc", 1 << 22, 64, 8, "MiMC chains, 2^22 steps x 64 columns, blowup 8 (LDE 32 GiB)"),
     "aggregation_16": ("aggregation", 32, 120, 16, "FedAvg aggregation AIR over 16 updates, 32 x 120 trace"),
 }
 
