@@ -371,9 +371,10 @@ def main():
             "prove_ms": ms_latency / args.steps,
             "roofline": {"bound": "hbm", "kernel": "k_ntt_pass (K1 interpolation + K2 coset LDE)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
-                         # dram__bytes_read+write of the two coset-LDE launches (ncu --set full, profiles/r1_ncu_ntt_lde_v1_radix8_regs.txt):
-                         # 2.9x the algorithmic bytes because n = 2^16 needs two passes through HBM (the tile of one pass is 2^8 rows)
-                         "traffic": 12.227e9 if args.workload == "training_2p16" else None, "peak_source": peak_src,
+                         # dram__bytes_read+write summed over the K1+K2 launches of one proof (transpose, 2 interpolation passes, 2 LDE
+                         # passes; ncu, profiles/r1_ncu_k1k2_dram_traffic.csv): 2.8x the algorithmic bytes because n = 2^16 needs two
+                         # passes through HBM per transform (a shared-memory tile holds 2^8 rows x 16 columns)
+                         "traffic": 13.566e9 if args.workload == "training_2p16" and not sharded else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_proof": alg["lde"], "kernel_ms_per_proof": lde_ms,
                          "note": "bound by the FMA-heavy (IMAD) pipe, not HBM: a radix-2 f128 butterfly is ~105 SASS integer instructions "
                                  "per 32 bytes moved; ncu: sm__pipe_fmaheavy_cycles_active 73%, DRAM 9-16% (profiles/r1_ncu_ntt_lde_v1_radix8_regs.txt)"},

@@ -319,3 +319,17 @@ def test_large_mimc_proof_verifies(gpu_ctx, oracle):
     bad = dict(air, assertions=air["assertions"][:-1] + [(air["assertions"][-1][0], air["assertions"][-1][1], 12345)])
     with pytest.raises(Z.VerifierError):
         Z.verify(proof, bad)
+
+
+def test_prove_batch_single_rank(gpu_ctx, oracle):
+    """multi_gpu.prove_batch (BASELINE configs[3]: a batch of independent proofs) on one rank: order preserved, all verify."""
+    from zk_stark_project_b200 import multi_gpu as M
+    jobs = []
+    for i in range(4):
+        p = Z.MimcProver(T.options(blowup=8, grinding=4), [50 * i + j + 1 for j in range(1 + i)], 128)
+        jobs.append((p, p.build_trace()))
+    proofs = M.prove_batch(jobs, gpu_ctx)
+    assert len(proofs) == 4 and len({M.digest(p) for p in proofs}) == 4
+    for (p, tr), proof in zip(jobs, proofs):
+        assert Z.verify(proof, p.describe(tr))
+        assert proof == oracle.prove(p.describe(tr), tr.to_bytes())[0]
