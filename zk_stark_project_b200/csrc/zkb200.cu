@@ -91,7 +91,17 @@ struct zkb_ctx {
     uint32_t tab_log_built = 0, pow3_for_log_n = 0, pow3_for_beta = 0;
     PowTab roots{}, inv3tab{};
     uint32_t inv3_l1 = 0;
-    cudaEvent_t ev[16];
+    // per-stage CUDA events; elapsed times are collected lazily (no host synchronisation inside a proof just for timing)
+    enum { TS_LDE, TS_XCHG, TS_LEAF, TS_MERKLE, TS_CONSTR, TS_COMP, TS_OOD, TS_DEEP, TS_FRI, TS_GRIND, TS_QUERY, TS_TOTAL, TS_COUNT };
+    cudaEvent_t tev[TS_COUNT][2];
+    bool trec[TS_COUNT] = {};
+    bool times_valid = true;
+    // pinned host staging for the small per-stage uploads (coefficients, challenges, positions): truly asynchronous H2D
+    uint8_t* h_stage = nullptr;
+    size_t h_stage_cap = 0, h_stage_used = 0;
+    // MiMC periodic-column table over the ce domain, cached across proofs of the same shape
+    std::vector<HF> per_cache, per_cache_params;
+    uint64_t per_cache_n = 0, per_cache_ce = 0;
     cudaEvent_t ev_group[17];          // per column group: "H2D of this group has landed"
     cudaStream_t copy_stream = nullptr;  // trace ingest overlaps the NTTs of earlier column groups
     bool ev_ok = false;
@@ -141,7 +151,9 @@ struct zkb_ctx {
         CK(cudaGetDeviceProperties(&prop, device));
         sm_count = prop.multiProcessorCount;
         CK(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        for (auto& x : ev) CK(cudaEventCreate(&x));
+        for (auto& pr : tev) for (auto& x : pr) CK(cudaEventCreate(&x));
+        h_stage_cap = (size_t)8 << 20;
+        CK(cudaHostAlloc((void**)&h_stage, h_stage_cap, cudaHostAllocDefault));
         for (auto& x : ev_group) CK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
         CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
         ev_ok = true;
@@ -157,10 +169,36 @@ struct zkb_ctx {
         if (comm) { g_nccl.CommDestroy(comm); comm = nullptr; }
         for (auto& b : d_fri_evals) b.release();
         for (auto& b : d_fri_tree) b.release();
-        if (ev_ok) { for (auto& x : ev) cudaEventDestroy(x); for (auto& x : ev_group) cudaEventDestroy(x); cudaStreamDestroy(copy_stream); }
+        if (ev_ok) { for (auto& pr : tev) for (auto& x : pr) cudaEventDestroy(x); for (auto& x : ev_group) cudaEventDestroy(x); cudaStreamDestroy(copy_stream); }
+        if (h_stage) cudaFreeHost(h_stage);
     }
 
     void h2d(void* dst, const void* src, size_t bytes) { CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream)); }
+    // small upload through the pinned staging area: returns immediately, `src` may be released right away.  The area is
+    // rewound at the start of every proof (every proof ends with a stream synchronisation).
+    void h2d_small(void* dst, const void* src, size_t bytes) {
+        if (bytes == 0) return;
+        const size_t need = (bytes + 255) & ~(size_t)255;
+        if (h_stage_used + need > h_stage_cap) {  // does not fit: plain (staged by the driver) copy, then wait so `src` can go away
+            CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+            CK(cudaStreamSynchronize(stream));
+            return;
+        }
+        memcpy(h_stage + h_stage_used, src, bytes);
+        CK(cudaMemcpyAsync(dst, h_stage + h_stage_used, bytes, cudaMemcpyHostToDevice, stream));
+        h_stage_used += need;
+    }
+    void t_begin(int st) { CK(cudaEventRecord(tev[st][0], stream)); }
+    void t_end(int st) { CK(cudaEventRecord(tev[st][1], stream)); trec[st] = true; times_valid = false; }
+    void collect_times() {
+        if (times_valid) return;
+        CK(cudaSetDevice(device));
+        CK(cudaStreamSynchronize(stream));
+        float* slot[TS_COUNT] = {&times.lde, &times.interpolate, &times.leaf_hash, &times.merkle, &times.constraints, &times.composition,
+                                 &times.ood, &times.deep, &times.fri, &times.grind, &times.queries, &times.total};
+        for (int st = 0; st < TS_COUNT; st++) if (trec[st]) CK(cudaEventElapsedTime(slot[st], tev[st][0], tev[st][1]));
+        times_valid = true;
+    }
     void d2h(void* dst, const void* src, size_t bytes) {
         CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
@@ -318,6 +356,9 @@ struct zkb_ctx {
         memset(&ts, 0, sizeof(ts));
         ts.comp_degree_ok = 1;
         memset(&times, 0, sizeof(times));
+        for (auto& r : trec) r = false;
+        times_valid = true;
+        h_stage_used = 0;
         coin.init(air.coin_seed());
         fri_layers = air.num_fri_layers();
         if (fri_layers > 16) throw InvalidArg("too many FRI layers");
@@ -342,7 +383,7 @@ struct zkb_ctx {
         d_bufA.ensure(n * w * 16); d_bufB.ensure(n * w * 16);
         d_lde.ensure(N * w * 16);
         d_tree.ensure(2 * N * 32);
-        CK(cudaEventRecord(ev[0], stream));
+        t_begin(TS_LDE);
         if (host_cols) {
             d_trace.ensure((size_t)w * n * 16);
             for (uint32_t j = 0; j < w; j++) if (!host_cols[j]) throw InvalidArg("null trace column");
@@ -378,24 +419,22 @@ struct zkb_ctx {
             Xform xl{d_polys, w, c0, d_lde.as<fe>(), w, c0, wc, log_n, false, true, log_N, false, HF()};
             lde_log_p = run_xform(xl, d_tmp1, d_tmp2);
         }
-        CK(cudaEventRecord(ev[3], stream));
+        t_end(TS_LDE);
         // K3: leaves
+        t_begin(TS_LEAF);
         k_hash_lde_rows<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(lde_mat(), d_tree.as<uint32_t>() + N * 8, 0, 0);
         check_launch();
-        CK(cudaEventRecord(ev[4], stream));
+        t_end(TS_LEAF);
         // K4: tree
+        t_begin(TS_MERKLE);
         build_merkle(d_tree.as<uint32_t>(), N);
-        CK(cudaEventRecord(ev[5], stream));
+        t_end(TS_MERKLE);
         Digest32 root;
         d2h(root.b, d_tree.as<uint32_t>() + 8, 32);
         parts.commitments.push_back(root);
         memcpy(ts.trace_root, root.b, 32);
         if (root_out) memcpy(root_out, root.b, 32);
-        // interpolation and LDE are interleaved per group: report them together under `lde`, `interpolate` = 0
-        times.h2d = 0; times.interpolate = 0;
-        CK(cudaEventElapsedTime(&times.lde, ev[0], ev[3]));
-        CK(cudaEventElapsedTime(&times.leaf_hash, ev[3], ev[4]));
-        CK(cudaEventElapsedTime(&times.merkle, ev[4], ev[5]));
+        // interpolation and LDE are interleaved per group: they are reported together under `lde`
         stage = ST_TRACE;
     }
     void trace_commit_device(const fe* d_src, uint8_t root_out[32]) { trace_commit(nullptr, d_src, root_out); }
@@ -441,7 +480,7 @@ struct zkb_ctx {
         if (air.id == ZKB_AIR_ID_AGGREGATION) throw InvalidArg("the aggregation AIR cannot be column-sharded (replicas only)");
         if (N / G < 2) throw InvalidArg("LDE domain too small to shard");
         mg_active = true;
-        CK(cudaEventRecord(ev[0], stream));
+        t_begin(TS_LDE);
         if (host_cols_local) d_src = upload_cols(host_cols_local, wl, n, d_trace);
         d_bufA.ensure(n * wl * 16); d_bufB.ensure(n * wl * 16);
         {
@@ -456,7 +495,8 @@ struct zkb_ctx {
         Xform xl{d_polys, wl, 0, d_lde.as<fe>(), wl, 0, wl, log_n, false, true, log_N, false, HF()};
         xl.log_shard = log_g;
         lde_log_p = run_xform(xl, d_tmp1, d_tmp2);
-        CK(cudaEventRecord(ev[3], stream));
+        t_end(TS_LDE);
+        t_begin(TS_XCHG);
         // NVLink transpose: column shards -> row shards
         d_lde_rows.ensure(N * wl * 16);
         const size_t chunk = (size_t)(N / G) * wl * 16;  // bytes
@@ -466,18 +506,20 @@ struct zkb_ctx {
             NK(g_nccl.Recv(d_lde_rows.as<uint8_t>() + q * chunk, chunk, ncclUint8, (int)q, comm, stream));
         }
         NK(g_nccl.GroupEnd());
-        CK(cudaEventRecord(ev[6], stream));
+        t_end(TS_XCHG);
+        t_begin(TS_LEAF);
         // K3/K4 on this rank's rows
         const uint64_t Nl = N / G;
         d_tree.ensure(2 * Nl * 32);
         k_hash_lde_rows<<<(unsigned)((Nl + 127) / 128), 128, 0, stream>>>(lde_rows_mat(), d_tree.as<uint32_t>() + Nl * 8, (uint64_t)mg_rank * Nl, 0);
         check_launch();
-        CK(cudaEventRecord(ev[4], stream));
+        t_end(TS_LEAF);
+        t_begin(TS_MERKLE);
         build_merkle(d_tree.as<uint32_t>(), Nl);
         // all-gather of the subtree roots; the cap is finished on the host by every rank
         d_gather.ensure(4096 + (size_t)G * 32);
         NK(g_nccl.AllGather(d_tree.as<uint8_t>() + 32, d_gather.as<uint8_t>(), 32, ncclUint8, comm, stream));
-        CK(cudaEventRecord(ev[5], stream));
+        t_end(TS_MERKLE);
         mg_cap.assign(2 * (size_t)G, Digest32{});
         d2h(mg_cap.data() + G, d_gather.p, (size_t)G * 32);
         for (uint32_t i = G - 1; i >= 1; i--) { uint8_t buf[64]; memcpy(buf, mg_cap[2 * i].b, 32); memcpy(buf + 32, mg_cap[2 * i + 1].b, 32); b3_hash_host(buf, 64, mg_cap[i].b); }
@@ -485,11 +527,7 @@ struct zkb_ctx {
         parts.commitments.push_back(root);
         memcpy(ts.trace_root, root.b, 32);
         if (root_out) memcpy(root_out, root.b, 32);
-        times.h2d = 0;
-        CK(cudaEventElapsedTime(&times.lde, ev[0], ev[3]));
-        CK(cudaEventElapsedTime(&times.interpolate, ev[3], ev[6]));  // reused slot: NVLink all-to-all time
-        CK(cudaEventElapsedTime(&times.leaf_hash, ev[6], ev[4]));
-        CK(cudaEventElapsedTime(&times.merkle, ev[4], ev[5]));
+        // (the `interpolate` slot of zkb_stage_times carries the NVLink all-to-all time of a sharded proof)
         stage = ST_TRACE;
     }
     // TraceLde::query for a sharded trace: every rank gathers the queried rows / authentication nodes it owns, the
@@ -517,8 +555,8 @@ struct zkb_ctx {
         d_gather.ensure(total);
         d_mg_b.ensure(mine * G);
         uint8_t* base = d_gather.as<uint8_t>();
-        h2d(base + o_pos, pos.data(), np * 4);
-        if (!flat.empty()) h2d(base + o_idx, local.data(), flat.size() * 8);
+        h2d_small(base + o_pos, pos.data(), np * 4);
+        if (!flat.empty()) h2d_small(base + o_idx, local.data(), flat.size() * 8);
         k_gather_lde_rows<<<(np * w + 127) / 128, 128, 0, stream>>>(lde_rows_mat(), (const uint32_t*)(base + o_pos), np, (fe*)(base + o_out));
         check_launch();
         if (!flat.empty()) {
@@ -574,15 +612,18 @@ struct zkb_ctx {
         { HF on = HF::from_u64(3).pow((u128)n), wb = HF::root_of_unity(log_beta);
           for (uint64_t kc = 0; kc < ce; kc++) zinv[kc] = (on * wb.pow((u128)(kc << (log_beta - log_ce))) - HF::raw(1)).inv(); }
         // periodic column over the ce domain (PeriodicValueTable): P_L(x^(n/L)) tabulated on 3^(n/L) * <w_{L*ce}>
-        std::vector<HF> per;
-        if (air.id == ZKB_AIR_ID_MIMC) {
+        if (air.id == ZKB_AIR_ID_MIMC && !(per_cache_n == n && per_cache_ce == ce && per_cache_params.size() == air.params.size() &&
+                                           std::equal(per_cache_params.begin(), per_cache_params.end(), air.params.begin()))) {
             const size_t L = air.params.size();
             std::vector<HF> poly = host_interpolate(air.params, HF::raw(1));
             const HF off = HF::from_u64(3).pow((u128)(n / L)), wl = HF::root_of_unity(log2u(L * ce));
-            per.resize(L * ce);
+            per_cache.resize(L * ce);
             HF x = off;
-            for (size_t t = 0; t < L * ce; t++) { HF acc; for (size_t q = L; q-- > 0;) acc = acc * x + poly[q]; per[t] = acc; x = x * wl; }
+            for (size_t t = 0; t < L * ce; t++) { HF acc; for (size_t q = L; q-- > 0;) acc = acc * x + poly[q]; per_cache[t] = acc; x = x * wl; }
+            per_cache_params = air.params; per_cache_n = n; per_cache_ce = ce;
         }
+        static const std::vector<HF> no_per;
+        const std::vector<HF>& per = air.id == ZKB_AIR_ID_MIMC ? per_cache : no_per;
         // pack the small arrays into one device buffer
         const uint32_t ntl = p.n_trans;
         size_t off_t = 0, off_c = off_t + (size_t)ntl * 16, off_v = off_c + (size_t)nl * 16, off_z = off_v + (size_t)nl * 16, off_p = off_z + ce * 16,
@@ -592,7 +633,7 @@ struct zkb_ctx {
         if (nl) { memcpy(&pack[off_c], acoef.data(), (size_t)nl * 16); memcpy(&pack[off_v], aval.data(), (size_t)nl * 16); memcpy(&pack[off_col], acol.data(), (size_t)nl * 4); }
         memcpy(&pack[off_z], zinv.data(), ce * 16); if (!per.empty()) memcpy(&pack[off_p], per.data(), per.size() * 16);
         d_aux.ensure(total);
-        h2d(d_aux.p, pack.data(), total);
+        h2d_small(d_aux.p, pack.data(), total);
         uint8_t* base = d_aux.as<uint8_t>();
         p.tcoef = (const fe*)(base + off_t); p.a_coef = (const fe*)(base + off_c); p.a_val = (const fe*)(base + off_v);
         p.zinv = (const fe*)(base + off_z); p.periodic = (const fe*)(base + off_p); p.a_col = (const uint32_t*)(base + off_col);
@@ -607,11 +648,10 @@ struct zkb_ctx {
         else if (points >= ((uint64_t)1 << 19)) k_eval_constraints<2><<<(unsigned)((points / 2 + 127) / 128), 128, 0, stream>>>(p);
         else k_eval_constraints<1><<<(unsigned)((points + 127) / 128), 128, 0, stream>>>(p);
         check_launch();
-        CK(cudaStreamSynchronize(stream));  // `pack` must outlive the copy
     }
     void constraints_eval(const HF& alpha, uint8_t* evals_out) {
         if (stage != ST_TRACE) throw StateError("zkb_constraints_eval: trace is not committed");
-        CK(cudaEventRecord(ev[0], stream));
+        t_begin(TS_CONSTR);
         const uint64_t n = air.n, ce = (uint64_t)1 << log_ce;
         d_comp_evals.ensure(n * ce * 16);
         if (!mg_active) {
@@ -636,17 +676,15 @@ struct zkb_ctx {
             check_launch();
             NK(g_nccl.AllGather(mine, d_comp_evals.p, sl * 16, ncclUint8, comm, stream));
         }
-        CK(cudaEventRecord(ev[1], stream));
+        t_end(TS_CONSTR);
         if (evals_out) d2h(evals_out, d_comp_evals.p, n * ce * 16);
-        CK(cudaEventSynchronize(ev[1]));
-        CK(cudaEventElapsedTime(&times.constraints, ev[0], ev[1]));
         stage = ST_EVAL;
     }
 
     // K6
     void constraints_commit(uint8_t root_out[32]) {
         if (stage != ST_EVAL) throw StateError("zkb_constraints_commit: constraints are not evaluated");
-        CK(cudaEventRecord(ev[0], stream));
+        t_begin(TS_COMP);
         const uint64_t n = air.n, N = air.lde_size(), cen = n << log_ce;
         // CompositionPoly::new: interpolate over 3*<w_{ce n}>, then split into c columns of n coefficients
         d_bufA.ensure(cen * 16);
@@ -685,13 +723,12 @@ struct zkb_ctx {
             check_launch();
         }
         build_merkle(d_comp_tree.as<uint32_t>(), N);
-        CK(cudaEventRecord(ev[1], stream));
+        t_end(TS_COMP);
         Digest32 root;
         d2h(root.b, d_comp_tree.as<uint32_t>() + 8, 32);
         parts.commitments.push_back(root);
         memcpy(ts.constraint_root, root.b, 32);
         if (root_out) memcpy(root_out, root.b, 32);
-        CK(cudaEventElapsedTime(&times.composition, ev[0], ev[1]));
         stage = ST_COMP;
     }
 
@@ -699,7 +736,7 @@ struct zkb_ctx {
     // all-gathers the 2*w_local evaluations.
     void ood_eval(const HF& z_) {
         if (stage != ST_COMP) throw StateError("zkb_ood_eval: constraint commitment is missing");
-        CK(cudaEventRecord(ev[0], stream));
+        t_begin(TS_OOD);
         z = z_; zg = z * HF::root_of_unity(log_n);
         const uint64_t n = air.n; const uint32_t w = air.w;
         const uint32_t wl = mg_active ? (w >> log_g) : w;   // columns of d_polys
@@ -717,7 +754,7 @@ struct zkb_ctx {
                o_hp = o_ood + 2 * (size_t)wl, o_ga = o_hp + (size_t)c * nt, total = o_ga + 2 * (size_t)w;
         d_small.ensure(total * 16);
         fe* sm = d_small.as<fe>();
-        h2d(sm + o_zp, zp.data(), zp.size() * 16);
+        h2d_small(sm + o_zp, zp.data(), zp.size() * 16);
         k_ood_partial<<<(nch + nsub - 1) / nsub, 256, 0, stream>>>(d_polys, (uint32_t)n, wl, R, log_wq, to_fe(z), to_fe(zg), sm + o_zp, sm + o_zp + nch,
                                                                    sm + o_pz, sm + o_pzg);
         check_launch();
@@ -745,16 +782,14 @@ struct zkb_ctx {
         }
         ood_h.assign(c, HF());
         for (uint32_t i = 0; i < c; i++) { HF s_; for (uint32_t t = 0; t < nt; t++) s_ = s_ + host[2 * (size_t)wl + (size_t)i * nt + t]; ood_h[i] = s_; }
-        CK(cudaEventRecord(ev[1], stream));
-        CK(cudaEventSynchronize(ev[1]));
-        CK(cudaEventElapsedTime(&times.ood, ev[0], ev[1]));
+        t_end(TS_OOD);
         stage = ST_OOD;
     }
 
     // K8
     void deep_compose(const HF& alpha) {
         if (stage != ST_OOD) throw StateError("zkb_deep_compose: OOD frame is missing");
-        CK(cudaEventRecord(ev[0], stream));
+        t_begin(TS_DEEP);
         deep_alpha = alpha;
         const uint64_t n = air.n, N = air.lde_size(); const uint32_t w = air.w;
         // DeepCompositionCoefficients::draw_algebraic: alpha^0.. for trace columns, continuing for H columns  [A.5]
@@ -764,7 +799,7 @@ struct zkb_ctx {
         for (uint32_t j = 0; j < w; j++) { az = az + g[j] * ood_cur[j]; azg = azg + g[j] * ood_next[j]; }
         for (uint32_t i = 0; i < c; i++) bz = bz + g[w + i] * ood_h[i];
         d_aux.ensure((w + c) * 16);
-        h2d(d_aux.p, g.data(), g.size() * 16);
+        h2d_small(d_aux.p, g.data(), g.size() * 16);
         d_ab.ensure(n * 2 * 16);
         if (!mg_active) {
             k_deep_combine<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(d_polys, (uint32_t)n, w, d_aux.as<fe>(), d_bufA.as<fe>(), c,
@@ -784,7 +819,6 @@ struct zkb_ctx {
             k_deep_add_h<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_ab.as<fe>(), (uint32_t)n, d_bufA.as<fe>(), c, d_aux.as<fe>() + w);
             check_launch();
         }
-        CK(cudaStreamSynchronize(stream));  // `g` must outlive the copy
         d_ab_lde.ensure(N * 2 * 16);
         d_deep.ensure(N * 16);
         if (!mg_coset()) {
@@ -811,9 +845,7 @@ struct zkb_ctx {
                                                                                mg_log_kc(), 4);
             check_launch();
         }
-        CK(cudaEventRecord(ev[1], stream));
-        CK(cudaEventSynchronize(ev[1]));
-        CK(cudaEventElapsedTime(&times.deep, ev[0], ev[1]));
+        t_end(TS_DEEP);
         if (d_fri_evals.size() < fri_layers + 1) { d_fri_evals.resize(fri_layers + 1); d_fri_tree.resize(fri_layers + 1); }
         fri_layer = 0; fri_committed = false;
         stage = ST_DEEP;
@@ -878,9 +910,9 @@ struct zkb_ctx {
         d_gather.ensure(4096);
         uint32_t* d_seed = d_gather.as<uint32_t>();
         unsigned long long* d_found = reinterpret_cast<unsigned long long*>(d_gather.as<uint8_t>() + 64);
-        h2d(d_seed, seed, 32);
+        h2d_small(d_seed, seed, 32);
         unsigned long long init = ~0ull;
-        h2d(d_found, &init, 8);
+        h2d_small(d_found, &init, 8);
         uint64_t base = 1;
         const uint64_t window = (uint64_t)1 << 22;
         for (;;) {
@@ -918,8 +950,8 @@ struct zkb_ctx {
                total = o_dig + flat.size() * 32 + 32;
         d_gather.ensure(total);
         uint8_t* base = d_gather.as<uint8_t>();
-        h2d(base + o_pos, pos.data(), np * 4);
-        if (!flat.empty()) h2d(base + o_idx, flat.data(), flat.size() * 8);
+        h2d_small(base + o_pos, pos.data(), np * 4);
+        if (!flat.empty()) h2d_small(base + o_idx, flat.data(), flat.size() * 8);
         const uint32_t th = np * width;
         if (which == 0) k_gather_lde_rows<<<(th + 127) / 128, 128, 0, stream>>>(lde_mat(), (const uint32_t*)(base + o_pos), np, (fe*)(base + o_rows));
         else if (which == 1) k_gather_lde_rows<<<(th + 127) / 128, 128, 0, stream>>>(comp_mat(), (const uint32_t*)(base + o_pos), np, (fe*)(base + o_rows));
@@ -959,7 +991,7 @@ struct zkb_ctx {
     std::vector<uint8_t> prove(const zkb_air_desc* desc, const uint8_t* const* cols, const fe* d_trace_in, uint64_t force_nonce,
                                bool sharded = false) {
         begin(desc);
-        CK(cudaEventRecord(ev[14], stream));
+        t_begin(TS_TOTAL);
         uint8_t root[32];
         if (sharded) trace_commit_mg(cols, d_trace_in, root);
         else if (d_trace_in) trace_commit_device(d_trace_in, root);
@@ -982,7 +1014,7 @@ struct zkb_ctx {
         HF da = coin.draw();                                 // get_deep_composition_coeffs
         da.to_bytes(ts.deep_alpha);
         deep_compose(da);
-        CK(cudaEventRecord(ev[2], stream));
+        t_begin(TS_FRI);
         for (uint32_t l = 0; l < fri_layers; l++) {          // FriProver::build_layers
             fri_commit_layer(root);
             coin.reseed(root);
@@ -991,9 +1023,11 @@ struct zkb_ctx {
         Digest32 rc;
         fri_remainder(&rc);
         coin.reseed(rc.b);
-        CK(cudaEventRecord(ev[3], stream));
+        t_end(TS_FRI);
+        t_begin(TS_GRIND);
         uint64_t nonce = force_nonce ? force_nonce : grind(coin.seed, air.grinding);  // grind_query_seed
-        CK(cudaEventRecord(ev[4], stream));
+        t_end(TS_GRIND);
+        t_begin(TS_QUERY);
         parts.nonce = nonce; ts.pow_nonce = nonce;
         positions = coin.draw_integers(air.num_queries, air.lde_size(), nonce);        // get_query_positions
         std::sort(positions.begin(), positions.end());
@@ -1013,12 +1047,8 @@ struct zkb_ctx {
             query(0, positions, parts.trace_rows, parts.trace_paths);
             query(1, positions, parts.comp_rows, parts.comp_paths);
         }
-        CK(cudaEventRecord(ev[15], stream));
-        CK(cudaEventSynchronize(ev[15]));
-        CK(cudaEventElapsedTime(&times.fri, ev[2], ev[3]));
-        CK(cudaEventElapsedTime(&times.grind, ev[3], ev[4]));
-        CK(cudaEventElapsedTime(&times.queries, ev[4], ev[15]));
-        CK(cudaEventElapsedTime(&times.total, ev[14], ev[15]));
+        t_end(TS_QUERY);
+        t_end(TS_TOTAL);
         stage = ST_QUERY;
         return serialize_proof(air, parts);
     }
@@ -1061,7 +1091,13 @@ int32_t zkb_ctx_create(int32_t device, void* stream, zkb_ctx** out) {
 void zkb_ctx_destroy(zkb_ctx* ctx) { if (ctx) { ctx->destroy(); delete ctx; } }
 const char* zkb_last_error(const zkb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
 uint64_t zkb_kernel_launches(const zkb_ctx* ctx) { return ctx ? ctx->launches : 0; }
-int32_t zkb_last_stage_times(const zkb_ctx* ctx, zkb_stage_times* out) { if (!ctx || !out) return ZKB_ERR_INVALID; *out = ctx->times; return ZKB_OK; }
+int32_t zkb_last_stage_times(const zkb_ctx* ctx, zkb_stage_times* out) {
+    if (!ctx || !out) return ZKB_ERR_INVALID;
+    zkb_ctx* c = const_cast<zkb_ctx*>(ctx);  // elapsed times are read from the recorded events on first request
+    int32_t rc = guarded(c, [&] { c->collect_times(); });
+    *out = ctx->times;
+    return rc;
+}
 void* zkb_host_alloc(size_t bytes) { void* p = nullptr; if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr; return p; }
 void zkb_host_free(void* p) { if (p) cudaFreeHost(p); }
 void zkb_free(void* p) { free(p); }
