@@ -53,7 +53,7 @@ def test_merkle_root(gpu_ctx, oracle, n):
     assert root.raw == oracle.merkle_root([leaves[i].tobytes() for i in range(n)])
 
 
-LDE_CASES = [(8, 1, 2), (8, 3, 8), (16, 5, 16), (32, 120, 16), (64, 17, 8), (128, 240, 16), (256, 16, 4), (512, 33, 2),
+LDE_CASES = [(512, 20, 4), (512, 50, 2), (256, 17, 16), (8, 1, 2), (8, 3, 8), (16, 5, 16), (32, 120, 16), (64, 17, 8), (128, 240, 16), (256, 16, 4), (512, 33, 2),
              (1024, 64, 8), (4096, 9, 16), (8192, 20, 8), (1 << 14, 2, 16), (1 << 16, 4, 4)]
 
 

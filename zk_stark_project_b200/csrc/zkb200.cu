@@ -276,10 +276,12 @@ struct zkb_ctx {
         bool scale; HF scale_by;
         uint32_t log_shard = 0;  // coset LDE only: split every panel into 2^log_shard slot chunks (multi-GPU send view)
         uint32_t coset_lo = 0, coset_cnt = 0;  // coset LDE only: evaluate cosets [lo, lo + cnt) (0 = all) into a buffer holding just those
+        uint32_t cj = 0;  // column-tile width; 0 = from ncols.  Column groups of one matrix must share it: it fixes the pass plan
+                          // and with it the panel size of the LDE layout
     };
     // returns log_p of the panel layout for LDEs (size of the last pass)
     uint32_t run_xform(const Xform& x, DevBuf& s1, DevBuf& s2) {
-        const uint32_t cj = pick_cj(x.ncols);
+        const uint32_t cj = x.cj ? x.cj : pick_cj(x.ncols);
         std::vector<uint32_t> bnd = plan_layers(x.log_len, cj);
         const uint32_t passes = (uint32_t)bnd.size();
         const uint64_t len = (uint64_t)1 << x.log_len;
@@ -372,14 +374,17 @@ struct zkb_ctx {
     // coset LDE.  Column groups are independent until the rows are hashed, so the host-to-device copy of group g+1
     // (copy stream) overlaps the transforms of group g, and a group's polynomials (n*16 elements) stay L2-resident
     // while all beta cosets are evaluated from them.
-    // Group width: 48 columns when the trace comes from the host (5 groups at w = 240: the first copy exposes < 1 ms, every
-    // launch still fills > 25 waves of resident blocks); one group when the trace is already in HBM (no launch tails).
+    // Group widths: a trace that is already in HBM is one group (no launch tails).  A host trace is cut into groups of
+    // 16, 32, 48, 48, ... columns: the first copy, which nothing can hide, is short (16 columns), later groups are wide enough
+    // that every launch still fills > 25 waves of resident blocks.
     void trace_commit(const uint8_t* const* host_cols, const fe* d_src, uint8_t root_out[32]) {
-        const uint32_t GROUP_W = host_cols ? 48u : air.w;
         if (stage != ST_BEGUN) throw StateError("zkb_trace_commit: call zkb_begin first");
         const uint64_t n = air.n, N = air.lde_size();
         const uint32_t w = air.w;
-        const uint32_t ngroups = (w + GROUP_W - 1) / GROUP_W;
+        std::vector<std::pair<uint32_t, uint32_t>> groups;  // (first column, width)
+        if (!host_cols) groups.push_back({0, w});
+        else for (uint32_t c0 = 0, step = 16; c0 < w; c0 += groups.back().second, step = std::min(step + 16, 48u)) groups.push_back({c0, std::min(step, w - c0)});
+        const uint32_t ngroups = (uint32_t)groups.size();
         d_bufA.ensure(n * w * 16); d_bufB.ensure(n * w * 16);
         d_lde.ensure(N * w * 16);
         d_tree.ensure(2 * N * 32);
@@ -392,7 +397,7 @@ struct zkb_ctx {
             CK(cudaStreamWaitEvent(copy_stream, ev_group[16], 0));
             if (ngroups > 16) throw InvalidArg("too many column groups");
             for (uint32_t g = 0; g < ngroups; g++) {
-                const uint32_t c0 = g * GROUP_W, wc = std::min(GROUP_W, w - c0);
+                const uint32_t c0 = groups[g].first, wc = groups[g].second;
                 bool contiguous = true;
                 for (uint32_t j = 1; j < wc; j++) if (host_cols[c0 + j] != host_cols[c0] + (size_t)j * n * 16) contiguous = false;
                 uint8_t* dst = d_trace.as<uint8_t>() + (size_t)c0 * n * 16;
@@ -405,7 +410,7 @@ struct zkb_ctx {
         d_polys = d_bufB.as<fe>();
         const HF n_inv = HF::from_u64(n).inv();
         for (uint32_t g = 0; g < ngroups; g++) {
-            const uint32_t c0 = g * GROUP_W, wc = std::min(GROUP_W, w - c0);
+            const uint32_t c0 = groups[g].first, wc = groups[g].second;
             if (host_cols) CK(cudaStreamWaitEvent(stream, ev_group[g], 0));
             {
                 dim3 grid((unsigned)((n + 31) / 32), (wc + 31) / 32), block(32, 8);
@@ -414,9 +419,11 @@ struct zkb_ctx {
             }
             // K1: interpolate (inverse NTT, scaled by 1/n) -> polys row-major [n][w]
             Xform xi{d_bufA.as<fe>(), w, c0, d_bufB.as<fe>(), w, c0, wc, log_n, true, false, 0, true, n_inv};
+            xi.cj = pick_cj(w);
             run_xform(xi, d_tmp1, d_tmp2);
             // K2: coset LDE into the panel layout
             Xform xl{d_polys, w, c0, d_lde.as<fe>(), w, c0, wc, log_n, false, true, log_N, false, HF()};
+            xl.cj = pick_cj(w);
             lde_log_p = run_xform(xl, d_tmp1, d_tmp2);
         }
         t_end(TS_LDE);
