@@ -333,3 +333,35 @@ def test_prove_batch_single_rank(gpu_ctx, oracle):
     for (p, tr), proof in zip(jobs, proofs):
         assert Z.verify(proof, p.describe(tr))
         assert proof == oracle.prove(p.describe(tr), tr.to_bytes())[0]
+
+
+def test_randomized_shape_sweep(gpu_ctx, oracle):
+    """Seeded sweep over trace shapes (length, width, blowup, AIR): every layout decision in the driver (pass plans, ragged
+    column tiles, ingest groups, panel sizes, FRI depth) is shape dependent, so proofs of many odd shapes are compared byte
+    for byte with the oracle."""
+    rng = random.Random(0xB200)
+    for case in range(36):
+        kind = rng.choice(["training", "training", "mimc"])
+        n = 1 << rng.randint(3, 12)
+        if kind == "mimc":
+            n = max(n, 64)
+            w = rng.choice([1, 2, 3, 5, 8, 13, 16, 17, 31, 33, 48, 49, 64, 65, 80])
+            blowup = rng.choice([8, 16, 32])
+            p = Z.MimcProver(Z.ProofOptions(rng.randint(1, 60), blowup, rng.randint(0, 8), Z.FieldExtension.NONE, 16, rng.choice([3, 7, 15])),
+                             [rng.randrange(P) for _ in range(w)], n)
+            raw = oracle.mimc_trace(p.seeds, n, p.rc)
+            trace = Z.TraceTable(np.frombuffer(raw, dtype=np.uint64).reshape(w, n, 2))
+            air = p.describe(trace)
+        else:
+            w = 2 * rng.randint(1, 127)
+            blowup = rng.choice([2, 4, 8, 16, 32, 64])
+            opts = Z.ProofOptions(rng.randint(1, 60), blowup, rng.randint(0, 8), Z.FieldExtension.NONE, 16, rng.choice([3, 7, 15]))
+            data = T.random_felts(w * n, 1000 + case).reshape(w, n, 2)
+            air = T.synthetic_training_air(n, opts, data)
+            trace = Z.TraceTable(data)
+        try:
+            _prove_both(gpu_ctx, oracle, air, trace)
+        except RuntimeError as e:
+            # the only legitimate verifier complaint for arbitrary option combinations (as in Winterfell): the remainder bound
+            # does not divide the degree along the FRI layers
+            assert "degree truncation" in str(e) or "remainder degree" in str(e), (case, kind, n, w, blowup, str(e))
