@@ -218,8 +218,8 @@ def main():
 
     kind, n, w, beta, desc = WORKLOADS[args.workload]
     sharded = args.sharded and world > 1
-    if args.sharded and kind != "mimc":
-        raise SystemExit("--sharded needs a MiMC workload (columns per GPU must be a power of two)")
+    if args.sharded and kind == "aggregation":
+        raise SystemExit("--sharded: the aggregation AIR couples columns i and i+60 and cannot be column-sharded")
     ctx = L.Context(local_rank)  # default stream: the same stream torch.cuda.Event records on
     seed_rank = 0 if sharded else rank  # a sharded proof is ONE trace shared by all ranks
     air, data, opts = build_workload(args.workload, 0x5EED0000 + seed_rank)
@@ -233,7 +233,7 @@ def main():
     if sharded:
         from zk_stark_project_b200 import multi_gpu as M
         M.init_sharded(ctx, rank, world, dist)
-        data = data[rank * w_local:(rank + 1) * w_local]
+        data = data[rank * w_local:(rank + 1) * w_local]  # (every rank built the same seeded trace; it keeps its columns)
     nbytes = w_local * n * 16
     pinned = L.PinnedBuffer(nbytes)
     pinned.view()[:] = np.ascontiguousarray(data).reshape(-1).view(np.uint8)

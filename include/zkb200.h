@@ -148,7 +148,8 @@ int32_t zkb_query(zkb_ctx* ctx, uint32_t which, const uint32_t* positions, uint3
  * local; an NCCL all-to-all over NVLink turns column shards into row shards for leaf hashing and the Merkle subtrees, whose
  * roots are all-gathered; constraint evaluation, OOD and DEEP are column-local partial sums combined by an all-gather.
  * `air` describes the WHOLE trace (global width, all assertions); `local_cols` holds this rank's w/G columns.
- * Every rank returns the same proof bytes.  G and w/G must be powers of two; the aggregation AIR is not shardable. */
+ * Every rank returns the same proof bytes.  G must be a power of two that divides w (and at most the LDE panel size);
+ * the aggregation AIR couples columns i and i+60 and is not shardable. */
 int32_t zkb_mg_unique_id(uint8_t out[128]);                                         /* ncclGetUniqueId, on rank 0 */
 int32_t zkb_mg_init(zkb_ctx* ctx, int32_t rank, int32_t world, const uint8_t id[128]); /* ncclCommInitRank (collective) */
 int32_t zkb_mg_prove(zkb_ctx* ctx, const zkb_air_desc* air, const uint8_t* const* local_cols, uint64_t force_nonce,

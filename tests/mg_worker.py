@@ -27,7 +27,7 @@ def main():
     dist.broadcast_object_list(ids, src=0)
     ctx.mg_init(rank, world, ids[0])
     cases = json.loads(sys.argv[1]) if len(sys.argv) > 1 else [["mimc", 64, 4096, 8], ["mimc", 16, 256, 8], ["training", 128, 1024, 16],
-                                                                ["mimc", 64, 1 << 16, 8]]
+                                                                ["training", 240, 512, 16], ["mimc", 24, 256, 8], ["mimc", 64, 1 << 16, 8]]
     results = []
     for kind, w, n, blowup in cases:
         opts = Z.ProofOptions(40, blowup, 16, Z.FieldExtension.NONE, 16, 7)

@@ -208,7 +208,7 @@ def test_column_sharded_proof_two_gpus():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     root = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
-    cases = '[["mimc", 64, 1024, 8], ["mimc", 16, 256, 8], ["training", 128, 512, 16]]'
+    cases = '[["mimc", 64, 1024, 8], ["mimc", 16, 256, 8], ["training", 128, 512, 16], ["training", 240, 256, 16], ["mimc", 6, 128, 8]]'
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29611", "tests/mg_worker.py", cases], cwd=root, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "mg ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

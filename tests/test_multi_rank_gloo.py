@@ -105,8 +105,11 @@ def _sharded_worker(rank, world, port, q):
 
 def test_two_rank_column_sharded_commitment():
     assert list(M.column_shard(64, 8, 3)) == list(range(24, 32)) and list(M.row_shard(1 << 10, 4, 1))[:2] == [256, 257]
+    assert list(M.column_shard(240, 8, 7)) == list(range(210, 240))  # the training width splits 8 x 30
     with pytest.raises(ValueError):
-        M.column_shard(240, 8, 0)  # 30 columns per GPU is not a power of two
+        M.column_shard(240, 7, 0)
+    with pytest.raises(ValueError):
+        M.column_shard(64, 6, 0)
     # heap ownership: N = 16 leaves, G = 4: depth <= 2 replicated, below that owned by leaf range
     assert M.node_owner(1, 16, 4) == (-1, 1) and M.node_owner(7, 16, 4) == (-1, 7)
     assert M.node_owner(8, 16, 4) == (0, 2) and M.node_owner(15, 16, 4) == (3, 3) and M.node_owner(16 + 5, 16, 4) == (1, 4 + 1)

@@ -95,9 +95,10 @@ __host__ __device__ __forceinline__ void b3_parent(const uint32_t l[8], const ui
 // BLAKE3 of `count` field elements (16 B each) read from base[j * stride]; this is
 // Blake3_256::hash_elements over a matrix row stored with an arbitrary element stride.
 // count <= 255 (TraceInfo width limit) => at most 4 chunks, handled with a two-slot CV stack.
-// Element e lives at base[(e >> log_blk) * blk_stride + (e & (2^log_blk - 1)) * stride] (log_blk = 31: one block).
+// Element e lives at base[(e / bw) * blk_stride + (e % bw) * stride]; bw_magic = ceil(2^16 / bw) makes the division a
+// multiply-shift (exact for e, bw <= 256).  One block: bw = 256, bw_magic = 256.
 __device__ __forceinline__ void b3_hash_elems(const fe* __restrict__ base, size_t stride, uint32_t count, uint32_t out[8],
-                                              uint32_t log_blk, size_t blk_stride) {
+                                              uint32_t bw, uint32_t bw_magic, size_t blk_stride) {
     const uint32_t nchunks = count <= 64 ? 1u : (count + 63u) / 64u;
     uint32_t st0[8], st1[8];
     for (uint32_t c = 0; c < nchunks; c++) {
@@ -114,8 +115,8 @@ __device__ __forceinline__ void b3_hash_elems(const fe* __restrict__ base, size_
             for (uint32_t q = 0; q < 4; q++) {
                 uint4 v = make_uint4(0, 0, 0, 0);
                 if (q < nb) {
-                    const uint32_t e = eb + q;
-                    v = *reinterpret_cast<const uint4*>(base + (size_t)(e >> log_blk) * blk_stride + (size_t)(e & ((1u << log_blk) - 1u)) * stride);
+                    const uint32_t e = eb + q, blk = (e * bw_magic) >> 16;
+                    v = *reinterpret_cast<const uint4*>(base + (size_t)blk * blk_stride + (size_t)(e - blk * bw) * stride);
                 }
                 m[4 * q] = v.x; m[4 * q + 1] = v.y; m[4 * q + 2] = v.z; m[4 * q + 3] = v.w;
             }

@@ -29,7 +29,7 @@ __device__ __forceinline__ fe powtab(const PowTab& t, uint32_t e) {
     return fe_mul(a, b);
 }
 
-// LDE matrix descriptor.  Single GPU: log_shard = 0, bw = w, log_bw = 31 and the layout is the panel layout above.
+// LDE matrix descriptor.  Single GPU: log_shard = 0, bw = w and the layout is the panel layout above.
 // Column-sharded multi-GPU proofs (G = 2^log_shard ranks) store the array as [G][panels][bw][P'] with P' = P/G = 2^log_p:
 //   send view (view = 0) on rank r: its bw = w/G columns, all rows; chunk index = slot div P' (the destination rank)
 //   recv view (view = 1) on rank q: all w columns, its rows (slots [q P', (q+1) P')); chunk index = column div bw (the source)
@@ -37,7 +37,7 @@ __device__ __forceinline__ fe powtab(const PowTab& t, uint32_t e) {
 struct LdeMat {
     fe* data;
     uint32_t log_n, log_beta, w, log_p;   // log_p: slots per stored chunk (P' = P >> log_shard)
-    uint32_t log_shard, bw, log_bw, view, q_self;
+    uint32_t log_shard, bw, bw_magic, view, q_self;   // bw_magic = ceil(2^16 / bw): j / bw == (j * bw_magic) >> 16 for j, bw <= 256
     uint64_t blk_stride;                  // elements between column blocks (recv view): panels * bw * P'
     uint32_t k0, log_kc;                  // cosets stored: k in [k0, k0 + 2^log_kc) (all of them: k0 = 0, log_kc = log_beta)
 };
@@ -52,7 +52,8 @@ __device__ __forceinline__ size_t lde_row_base(const LdeMat& m, uint32_t k, uint
     return (((size_t)chunk * np + panel) * m.bw << m.log_p) + (slot & ((1u << m.log_p) - 1u));
 }
 __device__ __forceinline__ size_t lde_col_off(const LdeMat& m, uint32_t j) {
-    return (size_t)(j >> m.log_bw) * m.blk_stride + ((size_t)(j & ((1u << m.log_bw) - 1u)) << m.log_p);
+    const uint32_t blk = (j * m.bw_magic) >> 16;
+    return (size_t)blk * m.blk_stride + ((size_t)(j - blk * m.bw) << m.log_p);
 }
 __device__ __forceinline__ size_t lde_addr(const LdeMat& m, uint32_t k, uint32_t i, uint32_t j) {
     return lde_row_base(m, k, i) + lde_col_off(m, j);
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(128) k_hash_lde_rows(const LdeMat m, uint32_t*
     // leaf index: global r = i*beta + k; compact (coset-sharded matrices): i * (stored cosets) + local coset
     const uint64_t r = compact ? (((uint64_t)i << m.log_kc) + (k - m.k0)) : (((uint64_t)i << m.log_beta) + k - leaf0);
     uint32_t d[8];
-    b3_hash_elems(m.data + lde_row_base(m, k, i), (size_t)1 << m.log_p, m.w, d, m.log_bw, m.blk_stride);
+    b3_hash_elems(m.data + lde_row_base(m, k, i), (size_t)1 << m.log_p, m.w, d, m.bw, m.bw_magic, m.blk_stride);
     uint4* o = reinterpret_cast<uint4*>(leaves + r * 8);
     o[0] = make_uint4(d[0], d[1], d[2], d[3]);
     o[1] = make_uint4(d[4], d[5], d[6], d[7]);
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(128) k_hash_strided_rows(const fe* __restrict_
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
     uint32_t d[8];
-    b3_hash_elems(e + i, rows, count, d, 31, 0);
+    b3_hash_elems(e + i, rows, count, d, 256, 256, 0);
     uint4* o = reinterpret_cast<uint4*>(leaves + i * 8);
     o[0] = make_uint4(d[0], d[1], d[2], d[3]);
     o[1] = make_uint4(d[4], d[5], d[6], d[7]);
@@ -735,7 +736,7 @@ __global__ void k_test_hash(const fe* data, uint32_t count, uint32_t nrows, uint
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nrows) return;
     uint32_t d[8];
-    b3_hash_elems(data + (size_t)i * count, 1, count, d, 31, 0);
+    b3_hash_elems(data + (size_t)i * count, 1, count, d, 256, 256, 0);
     for (int q = 0; q < 8; q++) out[i * 8 + q] = d[q];
 }
 

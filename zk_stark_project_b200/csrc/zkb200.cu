@@ -116,7 +116,8 @@ struct zkb_ctx {
 
     // ==========================================================================================================
     void count() { launches++; }
-    LdeMat std_mat(fe* data, uint32_t w, uint32_t log_p) const { return LdeMat{data, log_n, log_beta, w, log_p, 0, w, 31, 0, 0, 0, 0, log_beta}; }
+    static uint32_t magic16(uint32_t d) { return (65536u + d - 1) / d; }
+    LdeMat std_mat(fe* data, uint32_t w, uint32_t log_p) const { return LdeMat{data, log_n, log_beta, w, log_p, 0, w, magic16(w), 0, 0, 0, 0, log_beta}; }
     // coset-sharded matrices of a multi-GPU proof (composition columns, DEEP pair): rank r stores cosets [r*kc, (r+1)*kc)
     bool mg_coset() const { return mg_active && (uint32_t)mg_world <= air.blowup; }
     uint32_t mg_log_kc() const { return log_beta - log_g; }
@@ -128,13 +129,14 @@ struct zkb_ctx {
     // single GPU: the whole trace LDE; multi-GPU: the send view (this rank's columns, all rows)
     LdeMat lde_mat() const {
         if (!mg_active) return std_mat(d_lde.as<fe>(), air.w, lde_log_p);
-        return LdeMat{d_lde.as<fe>(), log_n, log_beta, air.w >> log_g, lde_log_p - log_g, log_g, air.w >> log_g, 31, 0, (uint32_t)mg_rank, 0, 0, log_beta};
+        const uint32_t wl = air.w / (uint32_t)mg_world;
+        return LdeMat{d_lde.as<fe>(), log_n, log_beta, wl, lde_log_p - log_g, log_g, wl, magic16(wl), 0, (uint32_t)mg_rank, 0, 0, log_beta};
     }
     // multi-GPU recv view: all columns, this rank's rows
     LdeMat lde_rows_mat() const {
-        const uint32_t wl = air.w >> log_g, lp = lde_log_p - log_g;
+        const uint32_t wl = air.w / (uint32_t)mg_world, lp = lde_log_p - log_g;
         const uint64_t np = (uint64_t)1 << (log_beta + log_n - lde_log_p);
-        return LdeMat{d_lde_rows.as<fe>(), log_n, log_beta, air.w, lp, log_g, wl, log2u(wl), 1, (uint32_t)mg_rank, (np * wl) << lp, 0, log_beta};
+        return LdeMat{d_lde_rows.as<fe>(), log_n, log_beta, air.w, lp, log_g, wl, magic16(wl), 1, (uint32_t)mg_rank, (np * wl) << lp, 0, log_beta};
     }
     LdeMat comp_mat() const { return coset_mat(d_comp_lde.as<fe>(), c, comp_log_p); }
     LdeMat ab_mat() const { return coset_mat(d_ab_lde.as<fe>(), 2, ab_log_p); }
@@ -483,7 +485,6 @@ struct zkb_ctx {
         const uint32_t w = air.w, G = (uint32_t)mg_world;
         if (w % G) throw InvalidArg("trace width must be divisible by the number of GPUs");
         const uint32_t wl = w / G;
-        if (!is_pow2(wl)) throw InvalidArg("columns per GPU must be a power of two");
         if (air.id == ZKB_AIR_ID_AGGREGATION) throw InvalidArg("the aggregation AIR cannot be column-sharded (replicas only)");
         if (N / G < 2) throw InvalidArg("LDE domain too small to shard");
         mg_active = true;
@@ -667,7 +668,7 @@ struct zkb_ctx {
             // column-sharded: partial evaluation over this rank's columns, all-gather, field sum
             // reduce-scatter by hand (NCCL cannot add mod p): slice q of every rank's partial vector goes to rank q, which
             // sums the G slices; the summed slices are all-gathered
-            const uint32_t wl = air.w >> log_g, G = (uint32_t)mg_world;
+            const uint32_t wl = air.w / (uint32_t)mg_world, G = (uint32_t)mg_world;
             const uint64_t total = n * ce, sl = total / G;
             d_mg_a.ensure(total * 16);
             d_mg_b.ensure(total * 16 + sl * 16);
@@ -746,7 +747,7 @@ struct zkb_ctx {
         t_begin(TS_OOD);
         z = z_; zg = z * HF::root_of_unity(log_n);
         const uint64_t n = air.n; const uint32_t w = air.w;
-        const uint32_t wl = mg_active ? (w >> log_g) : w;   // columns of d_polys
+        const uint32_t wl = mg_active ? (w / (uint32_t)mg_world) : w;   // columns of d_polys
         const uint32_t R = 64;
         const uint32_t nch = (uint32_t)((n + R - 1) / R);
         uint32_t log_wq = 0; while ((1u << log_wq) < wl) log_wq++;
@@ -814,7 +815,7 @@ struct zkb_ctx {
             check_launch();
         } else {
             // partial A over this rank's columns -> all-gather -> field sum -> add the (replicated) H part
-            const uint32_t wl = w >> log_g;
+            const uint32_t wl = w / (uint32_t)mg_world;
             d_mg_a.ensure(n * 2 * 16);
             d_mg_b.ensure(n * 2 * 16 * mg_world);
             k_deep_combine<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(d_polys, (uint32_t)n, wl, d_aux.as<fe>() + (size_t)mg_rank * wl,

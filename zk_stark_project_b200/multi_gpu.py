@@ -55,9 +55,9 @@ def digest(proof):
 
 # ---- column-sharded single proof (BASELINE.json configs[4]): index logic shared by the C++ driver and its tests ---------
 def column_shard(width, world_size, rank):
-    """Columns [r*w/G, (r+1)*w/G) of rank r; G and w/G must be powers of two (zkb_mg_prove)."""
-    if width % world_size or (width // world_size) & (width // world_size - 1) or world_size & (world_size - 1):
-        raise ValueError("width/world_size and world_size must be powers of two")
+    """Columns [r*w/G, (r+1)*w/G) of rank r; G must be a power of two dividing w (zkb_mg_prove)."""
+    if width % world_size or world_size & (world_size - 1):
+        raise ValueError("world_size must be a power of two that divides the trace width")
     wl = width // world_size
     return range(rank * wl, (rank + 1) * wl)
 
