@@ -20,9 +20,23 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION in this image) off it
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly one JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its version
+# banner there), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved original stdout.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
 
 import numpy as np  # noqa: E402
 
@@ -174,7 +188,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -192,6 +206,7 @@ def main():
                     help="ONE proof per step, column-sharded across all ranks (NVLink all-to-all; strong scaling) instead of one "
                          "independent proof per rank; MiMC workloads only (64 columns)")
     args = ap.parse_args()
+    capture_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -405,7 +420,7 @@ def main():
             line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "proofs/s", "ms_per_proof": dt * 1e3, "cores": cores, "kind": "port",
                                     "sample": "1 full proof of the same workload (C++ restatement of Winterfell's CPU prover, all host cores)",
                                     "proof_identical_to_gpu": ref == proof}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
