@@ -173,6 +173,14 @@ int32_t zkb_mimc_cipher_batch(zkb_ctx* ctx, const uint8_t* inputs, const uint8_t
  * w = count matrices [ac][fe], b = count vectors [ac]; benches/bench_mimc.rs:39-57 */
 int32_t zkb_mimc_hash_matrix_batch(zkb_ctx* ctx, const uint8_t* w, const uint8_t* b, uint32_t ac, uint32_t fe, const uint8_t* round_constants,
                                    uint32_t n_rc, uint64_t count, uint8_t* out);
+/* device-side training trace (src/training/prover.rs:90-218 without the PCIe ingest): the caller uploads the n_raw distinct raw
+ * state rows (n_raw = batch_size + 1, `half` = 120 values each); rows are [raw + mask || mask] with 64-bit masks generated on the
+ * device from `seed`.  Returns the device pointer (context-owned, column-major [2*half][n]) for zkb_prove_device and the first /
+ * last trace rows (2*half elements each) that get_pub_inputs needs (src/training/prover.rs:245-246). */
+int32_t zkb_training_trace_device(zkb_ctx* ctx, const uint8_t* raw_rows, uint32_t n_raw, uint32_t half, uint64_t n, uint64_t seed,
+                                  void** d_out, uint8_t* first_row_out, uint8_t* last_row_out);
+/* copy `bytes` bytes of context-owned device memory to the host (debugging / tests) */
+int32_t zkb_download(zkb_ctx* ctx, const void* d_src, uint64_t bytes, uint8_t* out);
 /* upload a column-major host trace into a context-owned device buffer (for device-resident timing) */
 int32_t zkb_upload_trace(zkb_ctx* ctx, const uint8_t* const* cols, uint32_t w, uint64_t n, void** d_out);
 

@@ -365,3 +365,33 @@ def test_randomized_shape_sweep(gpu_ctx, oracle):
             # the only legitimate verifier complaint for arbitrary option combinations (as in Winterfell): the remainder bound
             # does not divide the degree along the FRI layers
             assert "degree truncation" in str(e) or "remainder degree" in str(e), (case, kind, n, w, blowup, str(e))
+
+
+def test_device_side_training_trace(gpu_ctx, oracle):
+    """the training trace built on the GPU equals its host reconstruction (same raw states, same counter-based
+    masks) and proves / verifies like a host-built one."""
+    p = T.training_prover(3, T.options())
+    seed = 0xC0FFEE
+    dt = p.build_trace_device(seed=seed, ctx=gpu_ctx)
+    assert (dt.width(), dt.length()) == (240, 512)
+    host = dt.to_host()
+
+    def splitmix(x):
+        x = (x + 0x9E3779B97F4A7C15) & (2**64 - 1)
+        x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & (2**64 - 1)
+        x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & (2**64 - 1)
+        return x ^ (x >> 31)
+    states = p.raw_states()
+    assert len(states) == 4
+    for i in (0, 1, 2, 3, 4, 100, 511):
+        raw = states[min(i, 3)]
+        for j in (0, 1, 57, 119):
+            mask = splitmix(seed ^ splitmix((i * 0x100000001B3 + j) & (2**64 - 1)))
+            assert host.get(120 + j, i) == mask and host.get(j, i) == (raw[j] + mask) % P
+    assert [dt.get(c, 0) for c in range(240)] == [host.get(c, 0) for c in range(240)]
+    assert [dt.get(c, 511) for c in range(240)] == [host.get(c, 511) for c in range(240)]
+    proof = p.prove(dt)
+    air = p.describe(dt)
+    assert Z.verify(proof, air)
+    oracle.verify(air, proof.to_bytes())
+    assert proof.to_bytes() == oracle.prove(air, host.to_bytes())[0]

@@ -695,6 +695,35 @@ __global__ void k_mimc_trace(const fe* __restrict__ seeds, uint32_t w, uint64_t 
     }
 }
 
+// device-side training trace (src/training/prover.rs:117-130,188-199): row i = [raw_i + mask_i || mask_i] with
+// a fresh 64-bit mask per cell.  The raw state only changes during the first `n_raw - 1` steps (the batch), afterwards it is
+// constant (src/training/prover.rs:185), so the caller uploads n_raw rows of `half` raw values and the masks are generated
+// here with a counter-based generator (splitmix64 of (seed, row, column)); the reference draws them from an unseeded
+// thread_rng, so any generator is equally faithful.  Output: column-major [2*half][n].
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void k_training_trace(const fe* __restrict__ raw, uint32_t n_raw, uint32_t half, uint64_t n, uint64_t seed, fe* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t j = blockIdx.y;
+    if (i >= n) return;
+    const uint64_t m = splitmix64(seed ^ splitmix64(i * 0x100000001B3ull + j));
+    const fe mask = fe_from_u64(m);
+    const uint64_t r = i < n_raw ? i : (uint64_t)n_raw - 1;
+    fe_store(out + (size_t)j * n + i, fe_add(fe_load(raw + r * half + j), mask));
+    fe_store(out + (size_t)(half + j) * n + i, mask);
+}
+// read two rows of a column-major device trace (boundary rows for get_pub_inputs)
+__global__ void k_read_rows(const fe* __restrict__ trace, uint32_t w, uint64_t n, uint64_t r0, uint64_t r1, fe* __restrict__ out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= w) return;
+    fe_store(out + j, fe_load(trace + (size_t)j * n + r0));
+    fe_store(out + w + j, fe_load(trace + (size_t)j * n + r1));
+}
+
 // batched MiMC helpers of the reference: mimc_cipher (src/helper.rs:213-220) and mimc_hash_matrix (:222-233), one thread
 // per instance — the GPU counterpart of benches/bench_mimc.rs:17-57
 __device__ __forceinline__ fe mimc_cipher_dev(fe inp, const fe rc, const fe z) {

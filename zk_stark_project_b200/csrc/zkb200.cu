@@ -1298,6 +1298,32 @@ int32_t zkb_mimc_hash_matrix_batch(zkb_ctx* ctx, const uint8_t* w, const uint8_t
         ctx->d2h(out, base + count * per + n_rc, count * 16);
     });
 }
+int32_t zkb_training_trace_device(zkb_ctx* ctx, const uint8_t* raw_rows, uint32_t n_raw, uint32_t half, uint64_t n, uint64_t seed,
+                                  void** d_out, uint8_t* first_row_out, uint8_t* last_row_out) {
+    return guarded(ctx, [&] {
+        if (!raw_rows || !d_out || n_raw == 0 || half == 0 || half > 127 || n < n_raw) throw InvalidArg("bad training trace request");
+        CK(cudaSetDevice(ctx->device));
+        const uint32_t w = 2 * half;
+        ctx->d_user_trace.ensure((size_t)w * n * 16);
+        ctx->d_aux.ensure(((size_t)n_raw * half + 2 * w) * 16);
+        fe* d_raw = ctx->d_aux.as<fe>();
+        ctx->h2d(d_raw, raw_rows, (size_t)n_raw * half * 16);
+        dim3 grid((unsigned)((n + 255) / 256), half);
+        k_training_trace<<<grid, 256, 0, ctx->stream>>>(d_raw, n_raw, half, n, seed, ctx->d_user_trace.as<fe>());
+        ctx->check_launch();
+        fe* d_rows = d_raw + (size_t)n_raw * half;
+        k_read_rows<<<(w + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_user_trace.as<fe>(), w, n, 0, n - 1, d_rows);
+        ctx->check_launch();
+        std::vector<uint8_t> rows(2 * (size_t)w * 16);
+        ctx->d2h(rows.data(), d_rows, rows.size());
+        if (first_row_out) memcpy(first_row_out, rows.data(), (size_t)w * 16);
+        if (last_row_out) memcpy(last_row_out, rows.data() + (size_t)w * 16, (size_t)w * 16);
+        *d_out = ctx->d_user_trace.p;
+    });
+}
+int32_t zkb_download(zkb_ctx* ctx, const void* d_src, uint64_t bytes, uint8_t* out) {
+    return guarded(ctx, [&] { if (!d_src || !out) throw InvalidArg("null argument"); CK(cudaSetDevice(ctx->device)); ctx->d2h(out, d_src, bytes); });
+}
 int32_t zkb_upload_trace(zkb_ctx* ctx, const uint8_t* const* cols, uint32_t w, uint64_t n, void** d_out) {
     return guarded(ctx, [&] {
         if (!d_out) throw InvalidArg("null output");

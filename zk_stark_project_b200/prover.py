@@ -65,8 +65,16 @@ class Prover:
 
     def prove(self, trace, force_nonce=0):
         """`Prover::prove(trace)`: host trace in, proof out (the e2e path; H2D copy included)."""
+        from .trace import DeviceTrace
+        if isinstance(trace, DeviceTrace):  # built on the GPU: no ingest at all
+            air = self.describe(trace)
+            try:
+                proof, ts = trace.ctx.prove_device(air, trace.ptr, force_nonce)
+            except _lib.ZkbError as e:
+                raise ProverError(str(e)) from e
+            return Proof(proof, ts, trace.ctx.stage_times())
         if not isinstance(trace, TraceTable):
-            raise TypeError("trace must be a TraceTable")
+            raise TypeError("trace must be a TraceTable or a DeviceTrace")
         air = self.describe(trace)
         ctx = self.context()
         data = np.ascontiguousarray(trace.data)

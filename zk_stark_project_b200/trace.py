@@ -54,3 +54,29 @@ class TraceTable:
 
     def to_bytes(self):
         return self.data.tobytes()
+
+
+class DeviceTrace:
+    """A main trace segment that lives in GPU memory (column-major [width][length]), produced by a device-side trace builder.
+    Only the boundary rows, which `get_pub_inputs` reads back (src/training/prover.rs:245-246), are mirrored on the host."""
+
+    def __init__(self, ctx, ptr, width, length, first_row, last_row):
+        self.ctx, self.ptr, self._w, self._n = ctx, ptr, width, length
+        self._rows = {0: list(first_row), length - 1: list(last_row)}
+
+    def width(self):
+        return self._w
+
+    def length(self):
+        return self._n
+
+    def get(self, col, row):
+        if row not in self._rows:
+            raise IndexError("only the first and last rows of a device trace are mirrored on the host")
+        return self._rows[row][col]
+
+    def to_host(self):
+        """Copy the whole trace back (tests / debugging)."""
+        import numpy as np
+        raw = self.ctx.download(self.ptr, self._w * self._n * 16)
+        return TraceTable(np.frombuffer(raw, dtype=np.uint64).reshape(self._w, self._n, 2).copy())

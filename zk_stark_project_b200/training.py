@@ -142,12 +142,9 @@ class TrainingUpdateProver(Prover):
     def options(self):
         return self._options
 
-    def build_trace(self):
-        """src/training/prover.rs:90-218: row = [raw + mask || mask], fresh 64-bit masks every row."""
-        ac, fe = len(self.initial_b), len(self.initial_w[0])
-        flat_len = 2 * (ac * fe + ac)
-        n = self.trace_length
-
+    def raw_states(self):
+        """The distinct raw (unmasked) state rows of the trace: the initial state and one per processed sample
+        (src/training/prover.rs:100-115,136-183); rows past the batch repeat the last one (:185)."""
         def flatten(w, ws, b, bs):
             raw = []
             for row, srow in zip(w, ws):
@@ -160,24 +157,37 @@ class TrainingUpdateProver(Prover):
         w = [list(r) for r in self.initial_w]
         ws = [list(r) for r in self.w_sign]
         b, bs = list(self.initial_b), list(self.b_sign)
-        masks = self.rng.integers(0, 1 << 64, size=(n, flat_len), dtype=np.uint64)
-        data = np.empty((n, 2 * flat_len, 2), dtype=np.uint64)  # row-major first, transposed at the end
-        data[:, flat_len:, 0] = masks
-        data[:, flat_len:, 1] = 0
-        raw = flatten(w, ws, b, bs)
-        data[0:1, :flat_len] = _add_mod_rows(raw, masks[0:1])
-        last = min(self.batch_size, n - 1)
-        for step in range(1, last + 1):
-            s = step - 1
+        states = [flatten(w, ws, b, bs)]
+        for s in range(min(self.batch_size, self.trace_length - 1)):
             out, out_s = forward_propagation_layer(w, b, self.x_batch[s], ws, bs, self.x_batch_sign[s], self.precision)
             err, err_s = mse_prime(self.y_batch[s], out, out_s, self.precision)
             w, b, ws, bs = backward_propagation_layer(w, b, self.x_batch[s], err, self.learning_rate, self.precision, ws, bs,
                                                       self.x_batch_sign[s], err_s)
-            raw = flatten(w, ws, b, bs)
-            data[step:step + 1, :flat_len] = _add_mod_rows(raw, masks[step:step + 1])
-        if last + 1 < n:  # "If step > batch_size, just maintain the same state" (src/training/prover.rs:185)
-            data[last + 1:, :flat_len] = _add_mod_rows(raw, masks[last + 1:])
+            states.append(flatten(w, ws, b, bs))
+        return states
+
+    def build_trace(self):
+        """src/training/prover.rs:90-218: row = [raw + mask || mask], fresh 64-bit masks every row."""
+        states = self.raw_states()
+        flat_len, n = len(states[0]), self.trace_length
+        masks = self.rng.integers(0, 1 << 64, size=(n, flat_len), dtype=np.uint64)
+        data = np.empty((n, 2 * flat_len, 2), dtype=np.uint64)  # row-major first, transposed at the end
+        data[:, flat_len:, 0] = masks
+        data[:, flat_len:, 1] = 0
+        for i, raw in enumerate(states[:-1]):
+            data[i:i + 1, :flat_len] = _add_mod_rows(raw, masks[i:i + 1])
+        last = len(states) - 1  # "If step > batch_size, just maintain the same state" (src/training/prover.rs:185)
+        data[last:, :flat_len] = _add_mod_rows(states[-1], masks[last:])
         return TraceTable(np.ascontiguousarray(data.transpose(1, 0, 2)))
+
+    def build_trace_device(self, seed=0, ctx=None):
+        """The same trace built on the GPU: only the distinct raw states cross PCIe; the 64-bit masks come from a
+        counter-based generator on the device (the reference draws them from an unseeded thread_rng, src/training/prover.rs:117-121)."""
+        from .trace import DeviceTrace
+        ctx = ctx or self.context()
+        states = self.raw_states()
+        ptr, first, last = ctx.training_trace_device(states, self.trace_length, seed)
+        return DeviceTrace(ctx, ptr, 2 * len(states[0]), self.trace_length, first, last)
 
     def get_pub_inputs(self, trace):
         """src/training/prover.rs:235-267: the masked boundary rows are read back from the trace itself."""
