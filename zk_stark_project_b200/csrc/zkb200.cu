@@ -11,6 +11,7 @@
 #include <nccl.h>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <memory>
 #include "kernels.cuh"
 #include "host.hpp"
@@ -104,6 +105,7 @@ struct zkb_ctx {
     uint64_t per_cache_n = 0, per_cache_ce = 0;
     cudaEvent_t ev_group[17];          // per column group: "H2D of this group has landed"
     cudaStream_t copy_stream = nullptr;  // trace ingest overlaps the NTTs of earlier column groups
+    cudaStream_t xchg_stream = nullptr;  // sharded proofs: the NVLink all-to-all of finished coset batches overlaps the LDE of the next
     bool ev_ok = false;
 
     // ---- multi-GPU (column-sharded single proof) -----------------------------------------------------------------
@@ -158,6 +160,11 @@ struct zkb_ctx {
         CK(cudaHostAlloc((void**)&h_stage, h_stage_cap, cudaHostAllocDefault));
         for (auto& x : ev_group) CK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
         CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        {   // highest priority: the exchange's few blocks must get SM slots as soon as LDE blocks retire
+            int lo = 0, hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CK(cudaStreamCreateWithPriority(&xchg_stream, cudaStreamNonBlocking, hi));
+        }
         ev_ok = true;
         memset(&times, 0, sizeof(times));
     }
@@ -171,7 +178,7 @@ struct zkb_ctx {
         if (comm) { g_nccl.CommDestroy(comm); comm = nullptr; }
         for (auto& b : d_fri_evals) b.release();
         for (auto& b : d_fri_tree) b.release();
-        if (ev_ok) { for (auto& pr : tev) for (auto& x : pr) cudaEventDestroy(x); for (auto& x : ev_group) cudaEventDestroy(x); cudaStreamDestroy(copy_stream); }
+        if (ev_ok) { for (auto& pr : tev) for (auto& x : pr) cudaEventDestroy(x); for (auto& x : ev_group) cudaEventDestroy(x); cudaStreamDestroy(copy_stream); cudaStreamDestroy(xchg_stream); }
         if (h_stage) cudaFreeHost(h_stage);
     }
 
@@ -278,6 +285,8 @@ struct zkb_ctx {
         bool scale; HF scale_by;
         uint32_t log_shard = 0;  // coset LDE only: split every panel into 2^log_shard slot chunks (multi-GPU send view)
         uint32_t coset_lo = 0, coset_cnt = 0;  // coset LDE only: evaluate cosets [lo, lo + cnt) (0 = all) into a buffer holding just those
+        uint32_t batch_cosets = 0;  // coset LDE only: cosets per launch batch (0 = as many as the scratch budget allows)
+        std::function<void(uint32_t, uint32_t)> after_batch;  // called with (first coset, count) once a batch's last pass is enqueued
         uint32_t cj = 0;  // column-tile width; 0 = from ncols.  Column groups of one matrix must share it: it fixes the pass plan
                           // and with it the panel size of the LDE layout
     };
@@ -290,11 +299,11 @@ struct zkb_ctx {
         const uint32_t all_cosets = x.coset_lde ? (1u << (x.log_lde - x.log_len)) : 1;
         const uint32_t n_cosets = (x.coset_lde && x.coset_cnt) ? x.coset_cnt : all_cosets;
         // coset batches bound the scratch size
-        uint32_t batch = n_cosets;
+        uint32_t batch = x.batch_cosets ? std::min(x.batch_cosets, n_cosets) : n_cosets;
         if (passes > 1) {
             const uint64_t per = len * x.ncols * 16;
             uint64_t budget = (uint64_t)6 << 30;
-            batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_cosets, budget / std::max<uint64_t>(per, 1)));
+            batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(batch, budget / std::max<uint64_t>(per, 1)));
             s1.ensure(per * batch);
             if (passes > 2) s2.ensure(per * batch);
         }
@@ -327,6 +336,7 @@ struct zkb_ctx {
                 launch_pass(p);
                 a = bnd[q];
             }
+            if (x.after_batch) x.after_batch(x.coset_lo + k0, nk);
         }
         return bnd.back() - (passes > 1 ? bnd[passes - 2] : 0);
     }
@@ -502,18 +512,33 @@ struct zkb_ctx {
         d_lde.ensure(N * wl * 16);
         Xform xl{d_polys, wl, 0, d_lde.as<fe>(), wl, 0, wl, log_n, false, true, log_N, false, HF()};
         xl.log_shard = log_g;
+        // NVLink transpose, column shards -> row shards, pipelined behind the LDE.  In the send view [dest][coset][...] the
+        // data of one coset batch bound for one destination is contiguous, so a finished batch is shipped on xchg_stream
+        // while the next batch is still being evaluated; only the last batch's transfer is exposed.
+        d_lde_rows.ensure(N * wl * 16);
+        const size_t chunk = (size_t)(N / G) * wl * 16;  // bytes per (source, destination) pair
+        const size_t per_coset = chunk >> log_beta;
+        uint32_t n_batches = std::min<uint32_t>(air.blowup, 4);
+        while (n_batches > 1 && (uint64_t)n * wl * (air.blowup / n_batches) < ((uint64_t)1 << 20)) n_batches >>= 1;  // keep launches wide
+        xl.batch_cosets = (uint32_t)air.blowup / n_batches;
+        uint32_t shipped = 0;
+        xl.after_batch = [&](uint32_t k0, uint32_t nk) {
+            cudaEvent_t ev = ev_group[shipped++ & 15];
+            CK(cudaEventRecord(ev, stream));
+            CK(cudaStreamWaitEvent(xchg_stream, ev, 0));
+            NK(g_nccl.GroupStart());
+            for (uint32_t q = 0; q < G; q++) {
+                const size_t off = q * chunk + (size_t)k0 * per_coset;
+                NK(g_nccl.Send(d_lde.as<uint8_t>() + off, (size_t)nk * per_coset, ncclUint8, (int)q, comm, xchg_stream));
+                NK(g_nccl.Recv(d_lde_rows.as<uint8_t>() + off, (size_t)nk * per_coset, ncclUint8, (int)q, comm, xchg_stream));
+            }
+            NK(g_nccl.GroupEnd());
+        };
         lde_log_p = run_xform(xl, d_tmp1, d_tmp2);
         t_end(TS_LDE);
         t_begin(TS_XCHG);
-        // NVLink transpose: column shards -> row shards
-        d_lde_rows.ensure(N * wl * 16);
-        const size_t chunk = (size_t)(N / G) * wl * 16;  // bytes
-        NK(g_nccl.GroupStart());
-        for (uint32_t q = 0; q < G; q++) {
-            NK(g_nccl.Send(d_lde.as<uint8_t>() + q * chunk, chunk, ncclUint8, (int)q, comm, stream));
-            NK(g_nccl.Recv(d_lde_rows.as<uint8_t>() + q * chunk, chunk, ncclUint8, (int)q, comm, stream));
-        }
-        NK(g_nccl.GroupEnd());
+        CK(cudaEventRecord(ev_group[16], xchg_stream));
+        CK(cudaStreamWaitEvent(stream, ev_group[16], 0));
         t_end(TS_XCHG);
         t_begin(TS_LEAF);
         // K3/K4 on this rank's rows
