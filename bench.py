@@ -191,12 +191,92 @@ def run_reference(args, rank, world):
     emit(line)
 
 
+def run_mimc_helpers(args):
+    """GPU counterpart of the reference's criterion bench for its MiMC helpers (benches/bench_mimc.rs:17-57): `mimc_cipher`
+    (64 rounds of x <- (x + rc + z)^7, src/helper.rs:213-220) and `mimc_hash_matrix` over the bench's 6 x 9 weights + 6 biases
+    (60 chained ciphers, src/helper.rs:222-233).  criterion times ONE call; a GPU needs a batch, so every case is one
+    zkb_mimc_cipher_batch / zkb_mimc_hash_matrix_batch call through the C ABI with host buffers (copies inside the timed
+    region).  cpu_baseline is the restatement's single-call latency on one host core."""
+    import ctypes as C
+    import numpy as np
+    import zk_stark_project_b200 as Z
+    from zk_stark_project_b200 import lib as L
+    from zk_stark_project_b200 import synthetic as S
+
+    def felts(vals):
+        a = np.zeros((len(vals), 2), dtype=np.uint64)
+        for i, v in enumerate(vals):
+            a[i, 0], a[i, 1] = int(v) & 0xFFFFFFFFFFFFFFFF, int(v) >> 64
+        return a
+
+    def timed(fn):
+        for _ in range(max(args.warmup, 1)):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn()
+        return (time.perf_counter() - t0) / args.steps
+
+    ctx = L.Context(0)
+    lib = ctx.lib
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint8))
+    rc = Z.get_round_constants()
+    rc_arr = felts(rc)
+    x0, r0 = 0x1234567890ABCDEF, 0x0FEDCBA987654321  # u64-sized inputs as in benches/bench_mimc.rs:22-25
+    assert L.mimc_cipher_batch(ctx, [x0], [r0], [0])[0] == Z.mimc_cipher(x0, r0, 0)
+    cpu = None
+    if not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import pyoracle as O
+        assert O.mimc_cipher(x0, r0, 0) == Z.mimc_cipher(x0, r0, 0)
+        k = 20000
+        t0 = time.perf_counter()
+        for _ in range(k):
+            O.mimc_cipher(x0, r0, 0)
+        us = (time.perf_counter() - t0) / k * 1e6
+        cpu = {"value": 1e6 / us, "unit": "ciphers/s", "cores": 1, "kind": "port",
+               "sample": "%d single mimc_cipher calls through ctypes (call overhead included): %.2f us per call; "
+                         "mimc_hash_matrix = 60 chained ciphers = %.0f us" % (k, us, 60 * us)}
+    cases = []
+    head = None
+    for log_b in (0, 10, 16, 20, 22):
+        b = 1 << log_b
+        xs, rcs = S.random_felts(b, 7 + log_b), S.random_felts(b, 70 + log_b)
+        xs[:, 1] = 0
+        rcs[:, 1] = 0
+        zs = np.zeros((b, 2), dtype=np.uint64)
+        out = np.empty((b, 2), dtype=np.uint64)
+        dt = timed(lambda: ctx.check(lib.zkb_mimc_cipher_batch(ctx.handle, p(xs), p(rcs), p(zs), C.c_uint64(b), p(out))))
+        cases.append({"bench": "mimc_cipher", "batch": b, "call_ms": dt * 1e3, "ns_per_cipher": dt / b * 1e9, "ciphers_per_s": b / dt,
+                      "field_muls_per_s": b * 256 / dt})
+        if log_b == 20:
+            head = (b, dt)
+    ac, fe_n = 6, 9
+    w_one, b_one = felts([Z.f64_to_felt(42.0)] * (ac * fe_n)), felts([Z.f64_to_felt(1.0)] * ac)  # benches/bench_mimc.rs:41-42
+    want = Z.mimc_hash_matrix([[Z.f64_to_felt(42.0)] * fe_n] * ac, [Z.f64_to_felt(1.0)] * ac, rc)
+    for log_b in (0, 10, 16, 18):
+        b = 1 << log_b
+        ws, bs = np.tile(w_one, (b, 1)), np.tile(b_one, (b, 1))
+        out = np.empty((b, 2), dtype=np.uint64)
+        dt = timed(lambda: ctx.check(lib.zkb_mimc_hash_matrix_batch(ctx.handle, p(ws), p(bs), C.c_uint32(ac), C.c_uint32(fe_n), p(rc_arr),
+                                                                     C.c_uint32(len(rc)), C.c_uint64(b), p(out))))
+        assert (int(out[b - 1, 0]) | (int(out[b - 1, 1]) << 64)) == want, "mimc_hash_matrix mismatch"
+        cases.append({"bench": "mimc_hash_matrix", "batch": b, "call_ms": dt * 1e3, "us_per_hash": dt / b * 1e6, "hashes_per_s": b / dt})
+    b, dt = head
+    emit({"metric": "mimc_ciphers_per_sec", "value": b / dt, "unit": "ciphers/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+          "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u128 mod p (f128 field)",
+          "data": "synthetic", "config": {"workload": "mimc_helpers: batched mimc_cipher (headline: 2^20 per call) and mimc_hash_matrix 6x9+6",
+                                          "reference": "benches/bench_mimc.rs:17-57"},
+          "e2e": {"value": b / dt, "unit": "ciphers/s", "h2d_bytes_per_step": 48 * b, "d2h_bytes_per_step": 16 * b},
+          "gpu_launches": ctx.launches(), "cases": cases, "cpu_baseline": cpu})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="training_2p16", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="training_2p16", choices=sorted(WORKLOADS) + ["mimc_helpers"])
     ap.add_argument("--impl", default="zkb200", choices=["zkb200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle timing at N=1")
     ap.add_argument("--inflight", type=int, default=2,
@@ -211,6 +291,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "mimc_helpers":  # benches/bench_mimc.rs counterpart: helper kernels, not a proof
+        if rank == 0:
+            run_mimc_helpers(args)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
