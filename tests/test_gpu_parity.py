@@ -87,7 +87,8 @@ def _prove_both(gpu_ctx, oracle, air, trace):
     return proof_g
 
 
-@pytest.mark.parametrize("width,steps,blowup", [(1, 64, 8), (4, 64, 8), (64, 256, 8), (3, 1024, 16), (8, 1 << 14, 8)])
+@pytest.mark.parametrize("width,steps,blowup", [(1, 64, 8), (4, 64, 8), (64, 256, 8), (3, 1024, 16), (8, 1 << 14, 8),
+                                                (64, 1 << 13, 8)])  # the last one takes the boundary-polynomial path
 def test_mimc_proof_parity(gpu_ctx, oracle, width, steps, blowup):
     p = T.mimc_prover(width, steps, T.options(blowup=blowup))
     if steps <= 1024:
@@ -395,3 +396,17 @@ def test_device_side_training_trace(gpu_ctx, oracle):
     assert Z.verify(proof, air)
     oracle.verify(air, proof.to_bytes())
     assert proof.to_bytes() == oracle.prove(air, host.to_bytes())[0]
+
+
+def test_boundary_polynomial_path_forced():
+    """The evaluator takes boundary numerators either as per-point sums or as polynomials combined in coefficient space and
+    extended once; the library picks by cost.  ZKB_BOUNDARY_POLY=1 forces the polynomial path for every AIR and shape: the
+    proof-parity tests must still produce the oracle's bytes (the env var is read once per process, hence the subprocess)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, ZKB_BOUNDARY_POLY="1")
+    sel = "mimc_proof_parity or aggregation_proof_parity or training_proof_parity or edge_shapes or staged_api or randomized_shape_sweep"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k", sel, "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -359,7 +359,36 @@ struct EvalParams {
     uint32_t per_mask;
     PowTab roots; uint32_t log_tab;
     fe* out;                      // composition trace, natural ce-domain order
+    // boundary numerators as polynomials: bnd column g holds B_g(x) = sum_a coef_a (T_col_a(x) - value_a) over the ce domain
+    // (combined in coefficient space by k_boundary_combine, extended once); used when that is cheaper than per-point sums
+    uint32_t bnd_poly;
+    LdeMat bnd;
 };
+
+// B_g coefficients: bc[m][g] = sum_{a in group g} coef_a * polys[m][col_a]  (minus sum_a coef_a * value_a at m = 0);
+// one warp per coefficient row, lanes stride over the group's assertions
+struct BoundaryGroups { uint32_t n_groups; uint32_t g_off[ZKB_MAX_GROUPS + 1]; fe g_const[ZKB_MAX_GROUPS]; };
+__global__ void __launch_bounds__(256) k_boundary_combine(const fe* __restrict__ polys, uint32_t n, uint32_t w, const uint32_t* __restrict__ a_col,
+                                                          const fe* __restrict__ a_coef, const BoundaryGroups bg, fe* __restrict__ bc) {
+    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const fe* pr = polys + (size_t)row * w;
+    for (uint32_t g = 0; g < bg.n_groups; g++) {
+        fe s = fe_zero();
+        for (uint32_t a = bg.g_off[g] + lane; a < bg.g_off[g + 1]; a += 32) s = fe_add(s, fe_mul(fe_load(pr + __ldg(a_col + a)), fe_ldg(a_coef + a)));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            fe o;
+            o.x[0] = __shfl_down_sync(0xffffffffu, s.x[0], off); o.x[1] = __shfl_down_sync(0xffffffffu, s.x[1], off);
+            o.x[2] = __shfl_down_sync(0xffffffffu, s.x[2], off); o.x[3] = __shfl_down_sync(0xffffffffu, s.x[3], off);
+            s = fe_add(s, o);
+        }
+        if (lane == 0) {
+            if (row == 0) s = fe_sub(s, bg.g_const[g]);
+            fe_store(bc + (size_t)row * bg.n_groups + g, s);
+        }
+    }
+}
 
 // Each thread evaluates RPT points and shares ONE field inversion (Montgomery batch trick) between all their
 // boundary-divisor denominators: an inversion is ~250 multiplications, as much as the rest of a row's work.
@@ -419,11 +448,16 @@ __global__ void __launch_bounds__(128) k_eval_constraints(const EvalParams p) {
         tpart[s] = fe_mul(fe_mul(t, fe_sub(x, p.g_last)), fe_ldg(p.zinv + kc));
 
         // boundary groups: sum coef * (cur[col] - value), to be divided by (x - g^step)
+        const fe* bp = p.bnd_poly ? p.bnd.data + lde_row_base(p.bnd, kc, i) : nullptr;
         for (uint32_t g = 0; g < ng; g++) {
             fe sum = fe_zero();
-            for (uint32_t a = p.g_off[g]; a < p.g_off[g + 1]; a++) {
-                fe v = fe_sub(fe_load(cur + (size_t)__ldg(p.a_col + a) * cs), fe_ldg(p.a_val + a));
-                sum = fe_add(sum, fe_mul(fe_ldg(p.a_coef + a), v));
+            if (p.bnd_poly) {
+                sum = fe_load(bp + ((size_t)g << p.bnd.log_p));
+            } else {
+                for (uint32_t a = p.g_off[g]; a < p.g_off[g + 1]; a++) {
+                    fe v = fe_sub(fe_load(cur + (size_t)__ldg(p.a_col + a) * cs), fe_ldg(p.a_val + a));
+                    sum = fe_add(sum, fe_mul(fe_ldg(p.a_coef + a), v));
+                }
             }
             const uint32_t q = s * ZKB_MAX_GROUPS + g;
             num[q] = sum;

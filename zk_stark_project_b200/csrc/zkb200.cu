@@ -113,6 +113,7 @@ struct zkb_ctx {
     int mg_rank = 0, mg_world = 1;
     uint32_t log_g = 0;
     bool mg_active = false;             // the proof in flight is sharded
+    DevBuf d_bnd_coef, d_bnd_lde;       // boundary numerators as polynomials (constraints_eval_window)
     DevBuf d_lde_rows, d_mg_a, d_mg_b;  // recv view of the LDE; all-gather staging
     std::vector<Digest32> mg_cap;       // heap of the replicated top log G levels: cap[1] = root, cap[G + q] = subtree root q
 
@@ -173,7 +174,7 @@ struct zkb_ctx {
         cudaStreamSynchronize(stream);
         for (DevBuf* b : {&d_trace, &d_bufA, &d_bufB, &d_tmp1, &d_tmp2, &d_lde, &d_tree, &d_small, &d_comp_evals, &d_comp_lde, &d_comp_tree,
                           &d_ab, &d_ab_lde, &d_deep, &d_roots_lo, &d_roots_hi, &d_inv3_lo, &d_inv3_hi, &d_pow3, &d_aux, &d_gather, &d_user_trace,
-                          &d_lde_rows, &d_mg_a, &d_mg_b})
+                          &d_lde_rows, &d_mg_a, &d_mg_b, &d_bnd_coef, &d_bnd_lde})
             b->release();
         if (comm) { g_nccl.CommDestroy(comm); comm = nullptr; }
         for (auto& b : d_fri_evals) b.release();
@@ -675,6 +676,34 @@ struct zkb_ctx {
         p.k = air.id == ZKB_AIR_ID_AGGREGATION ? to_fe(air.params[0]) : fe{};
         p.roots = roots; p.log_tab = log_tab;
         p.out = out;
+        // Boundary numerators.  Per-point sums cost nl multiplications at each of the ce*n points; combining the asserted
+        // columns in coefficient space (nl per coefficient row) and extending the ng combined polynomials once costs
+        // nl*n + ng * ce*n * (log2(n)/2 + ~6).  MiMC on one GPU (128 assertions, ce = 8) is 2.7x cheaper that way; the training
+        // AIR (ce = 2) and narrow column shards are not, and tiny domains would only pay the extra launches.
+        p.bnd_poly = 0;
+        {
+            const uint64_t direct = (uint64_t)nl * ce * n, poly = (uint64_t)nl * n + (uint64_t)ng * ce * n * (log_n / 2 + 6);
+            static const char* force = getenv("ZKB_BOUNDARY_POLY");  // "0" / "1": A/B measurements and tests of both paths
+            const bool want = force ? (force[0] == '1') : (n * ce >= ((uint64_t)1 << 16) && direct > 2 * poly);
+            if (nl && want) {
+                BoundaryGroups bg{};
+                bg.n_groups = ng;
+                for (uint32_t gi = 0; gi <= ng; gi++) bg.g_off[gi] = p.g_off[gi];
+                for (uint32_t gi = 0; gi < ng; gi++) {
+                    HF cst;
+                    for (uint32_t a = p.g_off[gi]; a < p.g_off[gi + 1]; a++) cst = cst + acoef[a] * aval[a];
+                    bg.g_const[gi] = to_fe(cst);
+                }
+                d_bnd_coef.ensure(n * ng * 16);
+                d_bnd_lde.ensure(n * ce * ng * 16);
+                k_boundary_combine<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(d_polys, (uint32_t)n, ncols, p.a_col, p.a_coef, bg, d_bnd_coef.as<fe>());
+                check_launch();
+                Xform xb{d_bnd_coef.as<fe>(), ng, 0, d_bnd_lde.as<fe>(), ng, 0, ng, log_n, false, true, log_n + log_ce, false, HF()};
+                const uint32_t lp = run_xform(xb, d_tmp1, d_tmp2);
+                p.bnd_poly = 1;
+                p.bnd = LdeMat{d_bnd_lde.as<fe>(), log_n, log_ce, ng, lp, 0, ng, magic16(ng), 0, 0, 0, 0, log_ce};
+            }
+        }
         // rows per thread: share one inversion between 8 points once there are enough points to fill the GPU anyway
         const uint64_t points = n * ce;  // n >= 8 and ce >= 2: always a multiple of 8
         if (points >= ((uint64_t)1 << 21)) k_eval_constraints<8><<<(unsigned)((points / 8 + 127) / 128), 128, 0, stream>>>(p);
