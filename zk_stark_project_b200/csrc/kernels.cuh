@@ -188,17 +188,21 @@ __global__ void __launch_bounds__(256, 3) k_ntt_pass(const NttPass p) {
         if (p.coset) t = fe_mul(t, fe_ldg(p.pow3 + l));
         tw[q] = t;
     }
-    // load: row v of the tile is input row (u0 + (n/2^b) v) * 2^a + t_low; store bit-reversed
+    // load: row v of the tile is input row (u0 + (n/2^b) v) * 2^a + t_low; store bit-reversed.
+    // blockDim (256) is a multiple of cj, so a thread keeps its column and walks rows with a constant pointer stride.
     const uint32_t c_base = ct << log_cj;
-    const uint32_t E = S << log_cj;
+    const uint32_t jj_t = threadIdx.x & (cj - 1u), v_t = threadIdx.x >> log_cj, dv = blockDim.x >> log_cj;
+    const bool col_ok = c_base + jj_t < p.ncols;
     {
-        const fe* src = in + (((size_t)u0 << p.a) + t_low) * p.w_in + p.col0_in + c_base;
         const size_t vstride = ((size_t)p.w_in << (p.log_n - p.b)) << p.a;
-        for (uint32_t idx = threadIdx.x; idx < E; idx += blockDim.x) {
-            const uint32_t v = idx >> log_cj, jj = idx & (cj - 1u);
-            fe x = fe_zero();
-            if (c_base + jj < p.ncols) x = fe_load(src + (size_t)v * vstride + jj);
-            sm[bitrev(v, logS) * rs + jj] = x;
+        const fe* src = in + (((size_t)u0 << p.a) + t_low) * p.w_in + p.col0_in + c_base + jj_t + (size_t)v_t * vstride;
+        const size_t dstride = (size_t)dv * vstride;
+        fe* smc = sm + jj_t;
+        const uint32_t brs = (32u - logS) & 31u;  // logS == 0: the only row is v = 0 and brev(0) >> 0 == 0
+        if (col_ok) {
+            for (uint32_t v = v_t; v < S; v += dv, src += dstride) smc[(__brev(v) >> brs) * rs] = fe_load(src);
+        } else {  // columns past the end of a ragged last tile are zero-filled
+            for (uint32_t v = v_t; v < S; v += dv) smc[(__brev(v) >> brs) * rs] = fe_zero();
         }
     }
     __syncthreads();
@@ -212,27 +216,29 @@ __global__ void __launch_bounds__(256, 3) k_ntt_pass(const NttPass p) {
     }
     // store
     if (p.out_panel) {
-        // panel = k*2^a + t_low, slot = t_high; consecutive threads write consecutive slots of one column
+        // panel = k*2^a + t_low, slot = t_high; consecutive threads write consecutive slots of one column.  A thread keeps its
+        // slot(s) and walks columns: with S >= 256 every thread covers slots tid, tid + 256, .. of each column; smaller tiles put
+        // 256 / S columns side by side
         const size_t panel = ((size_t)(k - p.panel_k0) << p.a) + t_low;
         const uint32_t lp = logS - p.log_shard;                       // slots per stored chunk
         const size_t np = (size_t)1 << (p.log_kc + p.a);              // panels = stored cosets * 2^a
-        for (uint32_t idx = threadIdx.x; idx < E; idx += blockDim.x) {
-            const uint32_t jj = idx >> logS, th = idx & (S - 1u);
-            if (c_base + jj < p.ncols) {
-                const size_t chunk = th >> lp;
-                fe_store(p.out + (((chunk * np + panel) * p.w_out + p.col0_out + c_base + jj) << lp) + (th & ((1u << lp) - 1u)),
-                         sm[th * rs + jj]);
-            }
+        const size_t chunk_stride = (np * p.w_out) << lp;             // elements between slot chunks (multi-GPU send view)
+        const uint32_t th0 = threadIdx.x & (S - 1u), jj0 = logS >= 8 ? 0u : (threadIdx.x >> logS), djj = logS >= 8 ? 1u : (blockDim.x >> logS);
+        fe* colp = p.out + ((panel * p.w_out + p.col0_out + c_base + jj0) << lp);
+        for (uint32_t jj = jj0; jj < cj && c_base + jj < p.ncols; jj += djj, colp += (size_t)djj << lp) {
+            for (uint32_t th = (logS >= 8 ? threadIdx.x : th0); th < S; th += blockDim.x)
+                fe_store(colp + (size_t)(th >> lp) * chunk_stride + (th & ((1u << lp) - 1u)), sm[th * rs + jj]);
         }
     } else {
-        fe* dst = out + (((size_t)u0 << p.b) + t_low) * p.w_out + p.col0_out + c_base;
         const size_t tstride = (size_t)p.w_out << p.a;
-        for (uint32_t idx = threadIdx.x; idx < E; idx += blockDim.x) {
-            const uint32_t th = idx >> log_cj, jj = idx & (cj - 1u);
-            if (c_base + jj < p.ncols) {
-                fe x = sm[th * rs + jj];
+        fe* dst = out + (((size_t)u0 << p.b) + t_low) * p.w_out + p.col0_out + c_base + jj_t + (size_t)v_t * tstride;
+        const size_t dstride = (size_t)dv * tstride;
+        const fe* smc = sm + jj_t;
+        if (col_ok) {
+            for (uint32_t th = v_t; th < S; th += dv, dst += dstride) {
+                fe x = smc[th * rs];
                 if (p.do_scale) x = fe_mul(x, p.scale);
-                fe_store(dst + (size_t)th * tstride + jj, x);
+                fe_store(dst, x);
             }
         }
     }
