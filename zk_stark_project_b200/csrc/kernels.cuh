@@ -490,11 +490,20 @@ __global__ void __launch_bounds__(128) k_eval_constraints(const EvalParams p) {
 // polys row-major [n][w]; block c handles rows [c*R, (c+1)*R), thread j handles column j.
 // A block of 256 threads = nsub row-chunks x wq columns (wq = power of two >= w); chunk q covers rows [q*R, (q+1)*R).
 __global__ void __launch_bounds__(256) k_ood_partial(const fe* __restrict__ polys, uint32_t n, uint32_t w, uint32_t R, uint32_t log_wq,
-                                                      fe z, fe zg, const fe* __restrict__ zpow, const fe* __restrict__ zgpow,
+                                                      fe z, fe zg, fe zR, fe zgR,
                                                       fe* __restrict__ part_z, fe* __restrict__ part_zg) {
+    // z^(R c), (zg)^(R c) of each row chunk in the block: one thread per chunk raises z^R to the chunk index (<= 2 log2(n/R)
+    // multiplications, against 2 R wq for the chunk itself) instead of the host tabulating n/R powers per proof
+    __shared__ uint4 zs[2][256];
     const uint32_t j = threadIdx.x & ((1u << log_wq) - 1u), sub = threadIdx.x >> log_wq;
     const uint32_t c = blockIdx.x * (256u >> log_wq) + sub;
     const uint32_t m0 = c * R;
+    if (j == 0 && m0 < n) {
+        const fe a = fe_pow_u64(zR, c), b = fe_pow_u64(zgR, c);
+        zs[0][sub] = make_uint4(a.x[0], a.x[1], a.x[2], a.x[3]);
+        zs[1][sub] = make_uint4(b.x[0], b.x[1], b.x[2], b.x[3]);
+    }
+    __syncthreads();
     if (j >= w || m0 >= n) return;
     const uint32_t m1 = min(n, m0 + R);
     fe a = fe_zero(), b = fe_zero();
@@ -503,8 +512,11 @@ __global__ void __launch_bounds__(256) k_ood_partial(const fe* __restrict__ poly
         a = fe_add(fe_mul(a, z), v);
         b = fe_add(fe_mul(b, zg), v);
     }
-    fe_store(part_z + (size_t)c * w + j, fe_mul(a, fe_ldg(zpow + c)));
-    fe_store(part_zg + (size_t)c * w + j, fe_mul(b, fe_ldg(zgpow + c)));
+    fe pa, pb;
+    { const uint4 t = zs[0][sub]; pa.x[0] = t.x; pa.x[1] = t.y; pa.x[2] = t.z; pa.x[3] = t.w; }
+    { const uint4 t = zs[1][sub]; pb.x[0] = t.x; pb.x[1] = t.y; pb.x[2] = t.z; pb.x[3] = t.w; }
+    fe_store(part_z + (size_t)c * w + j, fe_mul(a, pa));
+    fe_store(part_zg + (size_t)c * w + j, fe_mul(b, pb));
 }
 // out[j] = sum_c part[c][j]; block = 32 columns x 32 chunk lanes, tree-reduced in shared memory
 __global__ void __launch_bounds__(1024) k_col_sum(const fe* __restrict__ part, uint32_t nchunks, uint32_t w, fe* __restrict__ out) {
@@ -537,7 +549,7 @@ __global__ void __launch_bounds__(256) k_poly_eval_partial(const fe* __restrict_
     const uint32_t m0 = t * Q, m1 = min(n, m0 + Q);
     fe a = fe_zero();
     for (uint32_t m = m1; m-- > m0;) a = fe_add(fe_mul(a, z), fe_load(c + m));
-    fe_store(part + (size_t)blockIdx.y * nt + t, fe_mul(a, fe_pow_u64(zQ, t)));
+    fe_store(part + (size_t)t * gridDim.y + blockIdx.y, fe_mul(a, fe_pow_u64(zQ, t)));  // [chunk][column], summed by k_col_sum
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -806,32 +806,38 @@ struct zkb_ctx {
         const uint32_t nch = (uint32_t)((n + R - 1) / R);
         uint32_t log_wq = 0; while ((1u << log_wq) < wl) log_wq++;
         const uint32_t nsub = 256u >> log_wq;
-        std::vector<HF> zp(2 * nch);
-        { HF zr = z.pow(R), zgr = zg.pow(R), a = HF::raw(1), b = HF::raw(1);
-          for (uint32_t q = 0; q < nch; q++) { zp[q] = a; zp[nch + q] = b; a = a * zr; b = b * zgr; } }
-        // layout of d_small: [zpow nch][zgpow nch][part_z nch*wl][part_zg nch*wl][ood 2wl][hpart c*nt][gathered 2w]
+        // layout of d_small: [part_z nch*wl][part_zg nch*wl][hpart nt*c][ood 2wl][ood_h c][gathered 2w]
         const uint32_t Q = 64;
         const uint32_t nt = (uint32_t)((n + Q - 1) / Q);
-        size_t o_zp = 0, o_pz = o_zp + 2 * (size_t)nch, o_pzg = o_pz + (size_t)nch * wl, o_ood = o_pzg + (size_t)nch * wl,
-               o_hp = o_ood + 2 * (size_t)wl, o_ga = o_hp + (size_t)c * nt, total = o_ga + 2 * (size_t)w;
+        size_t o_pz = 0, o_pzg = o_pz + (size_t)nch * wl, o_hp = o_pzg + (size_t)nch * wl, o_ood = o_hp + (size_t)c * nt,
+               o_ga = o_ood + 2 * (size_t)wl + c, o_sc = o_ga + 2 * (size_t)w, total = o_sc + 64 * 256;
         d_small.ensure(total * 16);
         fe* sm = d_small.as<fe>();
-        h2d_small(sm + o_zp, zp.data(), zp.size() * 16);
-        k_ood_partial<<<(nch + nsub - 1) / nsub, 256, 0, stream>>>(d_polys, (uint32_t)n, wl, R, log_wq, to_fe(z), to_fe(zg), sm + o_zp, sm + o_zp + nch,
+        // column sums of a [chunks][cols] matrix; many chunks are first folded 64-fold by treating the matrix as
+        // [chunks/64][64*cols], so the reduction is spread over 2*cols blocks instead of cols/32
+        auto col_sum = [&](const fe* part, uint32_t chunks, uint32_t cols, fe* out) {
+            if (chunks >= 4096 && chunks % 64 == 0) {
+                k_col_sum<<<(64 * cols + 31) / 32, dim3(32, 32), 0, stream>>>(part, chunks / 64, 64 * cols, sm + o_sc);
+                check_launch();
+                part = sm + o_sc; chunks = 64;
+            }
+            k_col_sum<<<(cols + 31) / 32, dim3(32, 32), 0, stream>>>(part, chunks, cols, out);
+            check_launch();
+        };
+        k_ood_partial<<<(nch + nsub - 1) / nsub, 256, 0, stream>>>(d_polys, (uint32_t)n, wl, R, log_wq, to_fe(z), to_fe(zg), to_fe(z.pow(R)), to_fe(zg.pow(R)),
                                                                    sm + o_pz, sm + o_pzg);
         check_launch();
-        k_col_sum<<<(wl + 31) / 32, dim3(32, 32), 0, stream>>>(sm + o_pz, nch, wl, sm + o_ood);
-        check_launch();
-        k_col_sum<<<(wl + 31) / 32, dim3(32, 32), 0, stream>>>(sm + o_pzg, nch, wl, sm + o_ood + wl);
-        check_launch();
+        col_sum(sm + o_pz, nch, wl, sm + o_ood);
+        col_sum(sm + o_pzg, nch, wl, sm + o_ood + wl);
         // H_i(z) from the composition column coefficients (still in d_bufA; replicated on every rank)
         {
             dim3 grid((nt + 255) / 256, c);
             k_poly_eval_partial<<<grid, 256, 0, stream>>>(d_bufA.as<fe>(), (uint32_t)n, Q, to_fe(z), to_fe(z.pow(Q)), sm + o_hp);
             check_launch();
+            col_sum(sm + o_hp, nt, c, sm + o_ood + 2 * (size_t)wl);
         }
-        std::vector<HF> host(2 * (size_t)wl + (size_t)c * nt);
-        d2h(host.data(), sm + o_ood, host.size() * 16);  // ood and hpart are adjacent
+        std::vector<HF> host(2 * (size_t)wl + c);
+        d2h(host.data(), sm + o_ood, host.size() * 16);  // the frame and the H values are adjacent
         ood_cur.assign(w, HF()); ood_next.assign(w, HF());
         if (!mg_active) {
             for (uint32_t j = 0; j < w; j++) { ood_cur[j] = host[j]; ood_next[j] = host[w + j]; }
@@ -843,7 +849,7 @@ struct zkb_ctx {
                 for (uint32_t jl = 0; jl < wl; jl++) { ood_cur[r * wl + jl] = all[(size_t)r * 2 * wl + jl]; ood_next[r * wl + jl] = all[(size_t)r * 2 * wl + wl + jl]; }
         }
         ood_h.assign(c, HF());
-        for (uint32_t i = 0; i < c; i++) { HF s_; for (uint32_t t = 0; t < nt; t++) s_ = s_ + host[2 * (size_t)wl + (size_t)i * nt + t]; ood_h[i] = s_; }
+        for (uint32_t i = 0; i < c; i++) ood_h[i] = host[2 * (size_t)wl + i];
         t_end(TS_OOD);
         stage = ST_OOD;
     }
