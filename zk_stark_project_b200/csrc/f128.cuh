@@ -185,7 +185,78 @@ __device__ __forceinline__ fe fe_mul(const fe& a, const fe& b) {
     mul_wide(a, b, w);
     return fe_reduce256(w);
 }
-__device__ __forceinline__ fe fe_sqr(const fe& a) { return fe_mul(a, a); }
+// 128-bit square -> 256 bits with 10 wide products instead of 16: the six off-diagonal products are summed once, doubled by a
+// one-bit funnel shift, and the four squares added on top
+__device__ __forceinline__ void sqr_wide(const fe& a, uint32_t r[8]) {
+    const uint32_t a0 = a.x[0], a1 = a.x[1], a2 = a.x[2], a3 = a.x[3];
+    uint32_t o1, o2, o3, o4, o5, o6, e2, e3, e4, e5;
+    asm("{\n\t"
+        "mul.lo.u32 %0, %10, %11;\n\t mul.hi.u32 %1, %10, %11;\n\t"      // a0 a1 @1
+        "mul.lo.u32 %2, %10, %13;\n\t mul.hi.u32 %3, %10, %13;\n\t"      // a0 a3 @3
+        "mul.lo.u32 %4, %12, %13;\n\t mul.hi.u32 %5, %12, %13;\n\t"      // a2 a3 @5
+        "mad.lo.cc.u32 %2, %11, %12, %2;\n\t madc.hi.cc.u32 %3, %11, %12, %3;\n\t"  // + a1 a2 @3
+        "addc.cc.u32 %4, %4, 0;\n\t addc.u32 %5, %5, 0;\n\t"
+        "mul.lo.u32 %6, %10, %12;\n\t mul.hi.u32 %7, %10, %12;\n\t"      // a0 a2 @2
+        "mul.lo.u32 %8, %11, %13;\n\t mul.hi.u32 %9, %11, %13;\n\t"      // a1 a3 @4
+        "}"
+        : "=&r"(o1), "=&r"(o2), "=&r"(o3), "=&r"(o4), "=&r"(o5), "=&r"(o6), "=&r"(e2), "=&r"(e3), "=&r"(e4), "=&r"(e5)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3));
+    // T = odd + even (limbs 1..7), then D = 2T
+    uint32_t t2, t3, t4, t5, t6, t7;
+    asm("add.cc.u32 %0, %6, %11;\n\t addc.cc.u32 %1, %7, %12;\n\t addc.cc.u32 %2, %8, %13;\n\t addc.cc.u32 %3, %9, %14;\n\t"
+        "addc.cc.u32 %4, %10, 0;\n\t addc.u32 %5, 0, 0;"
+        : "=r"(t2), "=r"(t3), "=r"(t4), "=r"(t5), "=r"(t6), "=r"(t7)
+        : "r"(o2), "r"(o3), "r"(o4), "r"(o5), "r"(o6), "r"(e2), "r"(e3), "r"(e4), "r"(e5));
+    const uint32_t d1 = o1 << 1, d2 = __funnelshift_l(o1, t2, 1), d3 = __funnelshift_l(t2, t3, 1), d4 = __funnelshift_l(t3, t4, 1),
+                   d5 = __funnelshift_l(t4, t5, 1), d6 = __funnelshift_l(t5, t6, 1), d7 = __funnelshift_l(t6, t7, 1);
+    uint32_t s0, s1, s2, s3, s4, s5, s6, s7;
+    asm("mul.lo.u32 %0, %8, %8;\n\t mul.hi.u32 %1, %8, %8;\n\t mul.lo.u32 %2, %9, %9;\n\t mul.hi.u32 %3, %9, %9;\n\t"
+        "mul.lo.u32 %4, %10, %10;\n\t mul.hi.u32 %5, %10, %10;\n\t mul.lo.u32 %6, %11, %11;\n\t mul.hi.u32 %7, %11, %11;"
+        : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3), "=r"(s4), "=r"(s5), "=r"(s6), "=r"(s7)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3));
+    r[0] = s0;
+    asm("add.cc.u32 %0, %7, %14;\n\t addc.cc.u32 %1, %8, %15;\n\t addc.cc.u32 %2, %9, %16;\n\t addc.cc.u32 %3, %10, %17;\n\t"
+        "addc.cc.u32 %4, %11, %18;\n\t addc.cc.u32 %5, %12, %19;\n\t addc.u32 %6, %13, %20;"
+        : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(s1), "r"(s2), "r"(s3), "r"(s4), "r"(s5), "r"(s6), "r"(s7), "r"(d1), "r"(d2), "r"(d3), "r"(d4), "r"(d5), "r"(d6), "r"(d7));
+}
+__device__ __forceinline__ fe fe_sqr(const fe& a) {
+    uint32_t w[8];
+    sqr_wide(a, w);
+    return fe_reduce256(w);
+}
+
+// Lazy sum of products: a 288-bit integer accumulator takes unreduced 256-bit products (up to 2^32 of them) and is reduced once.
+// Exact integer arithmetic, so the canonical result equals the sum of the individually reduced products.
+struct acc288 { uint32_t v[9]; };
+__device__ __forceinline__ void acc288_zero(acc288& a) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) a.v[i] = 0;
+}
+__device__ __forceinline__ void acc288_mad(acc288& a, const fe& x, const fe& y) {
+    uint32_t w[8];
+    mul_wide(x, y, w);
+    asm("add.cc.u32 %0, %0, %9;\n\t addc.cc.u32 %1, %1, %10;\n\t addc.cc.u32 %2, %2, %11;\n\t addc.cc.u32 %3, %3, %12;\n\t"
+        "addc.cc.u32 %4, %4, %13;\n\t addc.cc.u32 %5, %5, %14;\n\t addc.cc.u32 %6, %6, %15;\n\t addc.cc.u32 %7, %7, %16;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(a.v[0]), "+r"(a.v[1]), "+r"(a.v[2]), "+r"(a.v[3]), "+r"(a.v[4]), "+r"(a.v[5]), "+r"(a.v[6]), "+r"(a.v[7]), "+r"(a.v[8])
+        : "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]));
+}
+__device__ __forceinline__ fe acc288_reduce(const acc288& a) {
+    const fe lo = fe_reduce256(a.v);
+    // limb 8 carries weight 2^256 = C^2 = 2025*2^80 - 90*2^40 + 1 (mod p, and < 2^92 so the product below is canonical)
+    const uint32_t k0 = 0x00000001u, k1 = 0xFFFFA600u, k2 = 0x07E8FFFFu, t = a.v[8];
+    fe hi;
+    uint32_t m0, m1;
+    asm("mul.lo.u32 %0, %6, %7;\n\t mul.hi.u32 %1, %6, %7;\n\t"      // t k0 @0
+        "mul.lo.u32 %2, %6, %9;\n\t mul.hi.u32 %3, %6, %9;\n\t"      // t k2 @2
+        "mul.lo.u32 %4, %6, %8;\n\t mul.hi.u32 %5, %6, %8;"            // t k1 @1
+        : "=r"(hi.x[0]), "=r"(hi.x[1]), "=r"(hi.x[2]), "=r"(hi.x[3]), "=r"(m0), "=r"(m1)
+        : "r"(t), "r"(k0), "r"(k1), "r"(k2));
+    asm("add.cc.u32 %0, %0, %3;\n\t addc.cc.u32 %1, %1, %4;\n\t addc.u32 %2, %2, 0;"
+        : "+r"(hi.x[1]), "+r"(hi.x[2]), "+r"(hi.x[3]) : "r"(m0), "r"(m1));
+    return fe_add(lo, hi);
+}
 
 // a^e for a 128-bit exponent given as limbs (used for inversion and small fixed powers)
 __device__ __forceinline__ fe fe_pow_u64(fe b, uint64_t e) {

@@ -380,8 +380,9 @@ __global__ void __launch_bounds__(256) k_boundary_combine(const fe* __restrict__
     if (row >= n) return;
     const fe* pr = polys + (size_t)row * w;
     for (uint32_t g = 0; g < bg.n_groups; g++) {
-        fe s = fe_zero();
-        for (uint32_t a = bg.g_off[g] + lane; a < bg.g_off[g + 1]; a += 32) s = fe_add(s, fe_mul(fe_load(pr + __ldg(a_col + a)), fe_ldg(a_coef + a)));
+        acc288 acc; acc288_zero(acc);
+        for (uint32_t a = bg.g_off[g] + lane; a < bg.g_off[g + 1]; a += 32) acc288_mad(acc, fe_load(pr + __ldg(a_col + a)), fe_ldg(a_coef + a));
+        fe s = acc288_reduce(acc);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             fe o;
@@ -433,14 +434,15 @@ __global__ void __launch_bounds__(128) k_eval_constraints(const EvalParams p) {
         fe x = powtab(p.roots, r << (p.log_tab - log_N));
         { fe x2 = fe_add(x, x); x = fe_add(x2, x); }
 
-        // transition constraints, merged with their coefficients
-        fe t = fe_zero();
+        // transition constraints, merged with their coefficients.  sum_c coef_c * ev_c is accumulated as an exact 288-bit
+        // integer and reduced once per point (acc288): same field element, one reduction instead of one per column
+        acc288 tacc; acc288_zero(tacc);
         if (p.air_id == ZKB_AIR_AGGREGATION) {
             const uint32_t d = p.n_trans;
             for (uint32_t c = 0; c < d; c++) {
                 fe dn = fe_sub(fe_load(nxt + c * cs), fe_load(cur + c * cs));
                 fe ev = fe_sub(fe_mul(p.k, dn), fe_load(nxt + (size_t)(c + d) * cs));
-                t = fe_add(t, fe_mul(fe_ldg(p.tcoef + c), ev));
+                acc288_mad(tacc, fe_ldg(p.tcoef + c), ev);
             }
         } else if (p.air_id == ZKB_AIR_MIMC) {
             const fe rc = fe_ldg(p.periodic + (ci & p.per_mask));
@@ -448,9 +450,10 @@ __global__ void __launch_bounds__(128) k_eval_constraints(const EvalParams p) {
                 fe a1 = fe_add(fe_load(cur + c * cs), rc);
                 fe a2 = fe_sqr(a1), a4 = fe_sqr(a2), a6 = fe_mul(a4, a2), a7 = fe_mul(a6, a1);
                 fe ev = fe_sub(fe_load(nxt + c * cs), a7);
-                t = fe_add(t, fe_mul(fe_ldg(p.tcoef + c), ev));
+                acc288_mad(tacc, fe_ldg(p.tcoef + c), ev);
             }
         }  // TRAINING: every transition evaluation is zero (src/training/air.rs:274-278, src/helper.rs:141-146)
+        const fe t = acc288_reduce(tacc);
         tpart[s] = fe_mul(fe_mul(t, fe_sub(x, p.g_last)), fe_ldg(p.zinv + kc));
 
         // boundary groups: sum coef * (cur[col] - value), to be divided by (x - g^step)
@@ -460,10 +463,12 @@ __global__ void __launch_bounds__(128) k_eval_constraints(const EvalParams p) {
             if (p.bnd_poly) {
                 sum = fe_load(bp + ((size_t)g << p.bnd.log_p));
             } else {
+                acc288 bacc; acc288_zero(bacc);
                 for (uint32_t a = p.g_off[g]; a < p.g_off[g + 1]; a++) {
                     fe v = fe_sub(fe_load(cur + (size_t)__ldg(p.a_col + a) * cs), fe_ldg(p.a_val + a));
-                    sum = fe_add(sum, fe_mul(fe_ldg(p.a_coef + a), v));
+                    acc288_mad(bacc, fe_ldg(p.a_coef + a), v);
                 }
+                sum = acc288_reduce(bacc);
             }
             const uint32_t q = s * ZKB_MAX_GROUPS + g;
             num[q] = sum;
@@ -563,8 +568,9 @@ __global__ void __launch_bounds__(256) k_deep_combine(const fe* __restrict__ pol
                                                       const fe* __restrict__ gamma_h, fe* __restrict__ ab) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n) return;
-    fe s = fe_zero();
-    for (uint32_t j = lane; j < w; j += 32) s = fe_add(s, fe_mul(fe_load(polys + (size_t)warp * w + j), fe_ldg(gamma + j)));
+    acc288 acc; acc288_zero(acc);
+    for (uint32_t j = lane; j < w; j += 32) acc288_mad(acc, fe_load(polys + (size_t)warp * w + j), fe_ldg(gamma + j));
+    fe s = acc288_reduce(acc);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         fe o;
@@ -810,7 +816,16 @@ __global__ void k_test_field(const fe* a, const fe* b, fe* mul, fe* add, fe* sub
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     fe x = fe_load(a + i), y = fe_load(b + i);
-    fe_store(mul + i, fe_mul(x, y)); fe_store(add + i, fe_add(x, y)); fe_store(sub + i, fe_sub(x, y));
+    fe m = fe_mul(x, y);
+    {   // the lazy 288-bit accumulator and the dedicated squaring must agree with reduce-every-product arithmetic;
+        // a disagreement poisons the product the host checks
+        acc288 acc; acc288_zero(acc);
+        acc288_mad(acc, x, y); acc288_mad(acc, y, x); acc288_mad(acc, x, x); acc288_mad(acc, y, y); acc288_mad(acc, x, y);
+        const fe want = fe_add(fe_add(fe_add(m, m), m), fe_add(fe_mul(x, x), fe_mul(y, y)));
+        const fe sq = fe_add(fe_sqr(x), fe_sqr(y));
+        if (!fe_eq(acc288_reduce(acc), want) || !fe_eq(sq, fe_add(fe_mul(x, x), fe_mul(y, y)))) m.x[0] ^= 0xDEADBEEFu;
+    }
+    fe_store(mul + i, m); fe_store(add + i, fe_add(x, y)); fe_store(sub + i, fe_sub(x, y));
     fe_store(inv + i, fe_inv(x));
 }
 __global__ void k_test_hash(const fe* data, uint32_t count, uint32_t nrows, uint32_t* out) {
