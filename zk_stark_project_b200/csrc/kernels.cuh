@@ -107,6 +107,7 @@ struct NttPass {
     fe scale;
     PowTab roots;                  // w_{2^log_tab}^e
     const fe* pow3;                // pow3[l] = 3^(n >> l), l = 0..log_n
+    const fe* tw_tab;              // optional: precomputed tile twiddles [(k << a) + t_low][S - 1] (k_build_twiddles); null = generate
 };
 
 __device__ __forceinline__ uint32_t bitrev(uint32_t v, uint32_t bits) { return bits == 0 ? 0u : (__brev(v) >> (32 - bits)); }
@@ -143,6 +144,34 @@ __device__ __forceinline__ void ntt_unit(fe* __restrict__ col, const uint32_t rs
     for (int d = 0; d < R; d++) p[d * step] = x[d];
 }
 
+// twiddle q of the tile (coset k, t_low) of a pass: layer lam = floor(log2(q + 1)) + 1, position th = q + 1 - 2^(lam-1)
+__device__ __forceinline__ fe ntt_twiddle(const NttPass& p, uint32_t k, uint32_t t_low, uint32_t q) {
+    const uint32_t logS = p.b - p.a;
+    const uint32_t tab_mask = (1u << p.log_tab) - 1u;
+    const uint32_t lam = 32 - __clz(q + 1);      // 1..logS
+    const uint32_t th = q + 1 - (1u << (lam - 1));
+    const uint32_t l = p.a + lam;
+    (void)logS;
+    // exponent in units of w_{2^log_tab}
+    uint32_t e = (t_low << (p.log_tab - l)) + (th << (p.log_tab - lam));
+    if (p.coset) e += (k << (p.log_n - l)) << (p.log_tab - p.log_lde);
+    e &= tab_mask;
+    if (p.inverse) e = (0u - e) & tab_mask;
+    fe t = powtab(p.roots, e);
+    if (p.coset) t = fe_mul(t, fe_ldg(p.pow3 + l));
+    return t;
+}
+// all tile twiddles of a pass, for cosets [0, n_cosets): table[((k << a) + t_low) * (S - 1) + q]
+__global__ void k_build_twiddles(const NttPass p, fe* __restrict__ table) {
+    const uint32_t S = 1u << (p.b - p.a);
+    const uint64_t total = ((uint64_t)p.n_cosets << p.a) * (S - 1u);
+    const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total) return;
+    const uint32_t q = (uint32_t)(id % (S - 1u));
+    const uint32_t tile = (uint32_t)(id / (S - 1u));
+    fe_store(table + id, ntt_twiddle(p, tile >> p.a, tile & ((1u << p.a) - 1u), q));
+}
+
 template <int RHO>
 __device__ __forceinline__ void ntt_round(fe* sm, const fe* tw, uint32_t rs, uint32_t log_cj, uint32_t logS, uint32_t lam0) {
     const uint32_t cj_mask = (1u << log_cj) - 1u;
@@ -172,21 +201,12 @@ __global__ void __launch_bounds__(256, 3) k_ntt_pass(const NttPass p) {
     const uint32_t k = p.coset0 + kk;
     const fe* in = p.in + (size_t)kk * p.in_coset_stride;
     fe* out = p.out + (size_t)kk * p.out_coset_stride;
-    const uint32_t tab_mask = (1u << p.log_tab) - 1u;
-
     // twiddles: tw[2^(lam-1) - 1 + th] = s_l * w_{2^l}^{t_low} * w_{2^lam}^{th},  l = a + lam
-    for (uint32_t q = threadIdx.x; q + 1 < S; q += blockDim.x) {
-        const uint32_t lam = 32 - __clz(q + 1);      // 1..logS
-        const uint32_t th = q + 1 - (1u << (lam - 1));
-        const uint32_t l = p.a + lam;
-        // exponent in units of w_{2^log_tab}
-        uint32_t e = (t_low << (p.log_tab - l)) + (th << (p.log_tab - lam));
-        if (p.coset) e += (k << (p.log_n - l)) << (p.log_tab - p.log_lde);
-        e &= tab_mask;
-        if (p.inverse) e = (0u - e) & tab_mask;
-        fe t = powtab(p.roots, e);
-        if (p.coset) t = fe_mul(t, fe_ldg(p.pow3 + l));
-        tw[q] = t;
+    if (p.tw_tab) {
+        const fe* t = p.tw_tab + ((size_t)(k << p.a) + t_low) * (S - 1u);
+        for (uint32_t q = threadIdx.x; q + 1 < S; q += blockDim.x) tw[q] = fe_ldg(t + q);
+    } else {
+        for (uint32_t q = threadIdx.x; q + 1 < S; q += blockDim.x) tw[q] = ntt_twiddle(p, k, t_low, q);
     }
     // load: row v of the tile is input row (u0 + (n/2^b) v) * 2^a + t_low; store bit-reversed.
     // blockDim (256) is a multiple of cj, so a thread keeps its column and walks rows with a constant pointer stride.

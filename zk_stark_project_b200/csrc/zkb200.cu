@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <functional>
+#include <map>
+#include <tuple>
 #include <memory>
 #include "kernels.cuh"
 #include "host.hpp"
@@ -179,6 +181,7 @@ struct zkb_ctx {
         if (comm) { g_nccl.CommDestroy(comm); comm = nullptr; }
         for (auto& b : d_fri_evals) b.release();
         for (auto& b : d_fri_tree) b.release();
+        for (auto& kv : tw_cache) kv.second.release();
         if (ev_ok) { for (auto& pr : tev) for (auto& x : pr) cudaEventDestroy(x); for (auto& x : ev_group) cudaEventDestroy(x); cudaStreamDestroy(copy_stream); cudaStreamDestroy(xchg_stream); }
         if (h_stage) cudaFreeHost(h_stage);
     }
@@ -265,6 +268,32 @@ struct zkb_ctx {
         for (uint32_t q = 0; q < passes; q++) { uint32_t take = (log_len - done + (passes - q) - 1) / (passes - q); done += take; b.push_back(done); }
         return b;
     }
+    // Tile twiddles depend only on (transform size, layer range, coset, t_low): tables of up to 64 MiB are built once per shape
+    // (k_build_twiddles) and re-read from L2 by every column tile, column group and proof instead of being regenerated
+    // (two multiplications per twiddle) by each of the thousands of tiles that share them.
+    std::map<std::tuple<uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t>, DevBuf> tw_cache;
+    size_t tw_cache_bytes = 0;
+    const fe* twiddle_table(const NttPass& p, uint32_t all_cosets) {
+        const uint32_t S = 1u << (p.b - p.a);
+        const uint64_t entries = ((uint64_t)all_cosets << p.a) * (S - 1u), bytes = entries * 16;
+        if (S < 2 || bytes > ((uint64_t)64 << 20)) return nullptr;
+        const auto key = std::make_tuple(p.log_n, p.a, p.b, p.coset, p.inverse, p.coset ? p.log_lde : 0u);
+        auto it = tw_cache.find(key);
+        if (it != tw_cache.end()) return it->second.as<fe>();
+        if (tw_cache_bytes + bytes > ((uint64_t)256 << 20)) {  // a long-lived context that has seen many shapes: start over
+            CK(cudaStreamSynchronize(stream));
+            for (auto& kv : tw_cache) kv.second.release();
+            tw_cache.clear(); tw_cache_bytes = 0;
+        }
+        DevBuf& b = tw_cache[key];
+        b.ensure(bytes);
+        tw_cache_bytes += bytes;
+        NttPass q = p;
+        q.n_cosets = all_cosets; q.coset0 = 0; q.tw_tab = nullptr;
+        k_build_twiddles<<<(unsigned)((entries + 255) / 256), 256, 0, stream>>>(q, b.as<fe>());
+        check_launch();
+        return b.as<fe>();
+    }
     void launch_pass(NttPass& p) {
         const uint32_t S = 1u << (p.b - p.a);
         const uint32_t rs = p.cj + (p.cj > 1 ? 1 : 0);
@@ -322,6 +351,7 @@ struct zkb_ctx {
                 p.coset = x.coset_lde ? 1 : 0; p.inverse = x.inverse ? 1 : 0;
                 p.log_tab = log_tab; p.log_lde = x.coset_lde ? x.log_lde : 0;
                 p.roots = roots; p.pow3 = d_pow3.as<fe>();
+                p.tw_tab = twiddle_table(p, all_cosets);
                 if (last) {
                     p.out = x.out; p.w_out = x.w_out; p.col0_out = x.col0_out;
                     p.out_panel = x.coset_lde ? 1 : 0;
