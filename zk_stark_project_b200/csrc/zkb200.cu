@@ -1082,6 +1082,71 @@ struct zkb_ctx {
         paths = batch_proof_bytes(depth, plan, host.data() + (size_t)np * width * 16);
     }
 
+    // All openings of a single-GPU proof in one go: every gather kernel is enqueued into its own region of d_gather and ONE
+    // device-to-host copy (one synchronisation) brings rows and authentication nodes back, instead of one round trip per
+    // commitment (trace, composition, every FRI layer).
+    struct QueryReq { uint32_t which; const std::vector<uint32_t>* pos; std::vector<uint8_t>* rows; std::vector<uint8_t>* paths; };
+    void query_all(const std::vector<QueryReq>& reqs) {
+        struct Job { uint32_t width, depth, np; uint64_t domain; const uint32_t* heap; std::vector<std::vector<uint64_t>> plan; size_t nflat, o_pos, o_idx, o_out; };
+        std::vector<Job> jobs(reqs.size());
+        std::vector<uint8_t> up;      // positions and node indices of all jobs, one upload
+        size_t out_bytes = 0;
+        auto pad16 = [](size_t x) { return (x + 15) / 16 * 16; };
+        for (size_t q = 0; q < reqs.size(); q++) {
+            const QueryReq& r = reqs[q]; Job& j = jobs[q];
+            j.np = (uint32_t)r.pos->size();
+            if (j.np == 0 || j.np > 255) throw InvalidArg("bad number of query positions");
+            if (r.which == 0) { j.width = air.w; j.domain = air.lde_size(); j.heap = d_tree.as<uint32_t>(); }
+            else if (r.which == 1) { j.width = c; j.domain = air.lde_size(); j.heap = d_comp_tree.as<uint32_t>(); }
+            else {
+                const uint32_t l = r.which - 2;
+                if (l >= fri_layers) throw InvalidArg("no such FRI layer");
+                j.width = 16; j.domain = fri_domain(l) / 16; j.heap = d_fri_tree[l].as<uint32_t>();
+            }
+            for (uint32_t p : *r.pos) if (p >= j.domain) throw InvalidArg("query position out of range");
+            j.depth = log2u(j.domain);
+            j.plan = plan_batch_proof(j.depth, *r.pos);
+            std::vector<uint64_t> flat;
+            for (auto& v : j.plan) flat.insert(flat.end(), v.begin(), v.end());
+            j.nflat = flat.size();
+            j.o_pos = up.size(); up.resize(pad16(up.size() + (size_t)j.np * 4)); memcpy(&up[j.o_pos], r.pos->data(), (size_t)j.np * 4);
+            j.o_idx = up.size(); up.resize(pad16(up.size() + j.nflat * 8 + 8)); if (j.nflat) memcpy(&up[j.o_idx], flat.data(), j.nflat * 8);
+            j.o_out = out_bytes; out_bytes += pad16((size_t)j.np * j.width * 16 + j.nflat * 32);
+        }
+        const size_t o_out0 = pad16(up.size());
+        d_gather.ensure(o_out0 + out_bytes + 32);
+        uint8_t* base = d_gather.as<uint8_t>();
+        h2d_small(base, up.data(), up.size());
+        for (size_t q = 0; q < reqs.size(); q++) {
+            const Job& j = jobs[q];
+            const uint32_t which = reqs[q].which, th = j.np * j.width;
+            const uint32_t* dpos = (const uint32_t*)(base + j.o_pos);
+            fe* drows = (fe*)(base + o_out0 + j.o_out);
+            if (which == 0) k_gather_lde_rows<<<(th + 127) / 128, 128, 0, stream>>>(lde_mat(), dpos, j.np, drows);
+            else if (which == 1) k_gather_lde_rows<<<(th + 127) / 128, 128, 0, stream>>>(comp_mat(), dpos, j.np, drows);
+            else {
+                const uint32_t l = which - 2;
+                const fe* e = l == 0 ? d_deep.as<fe>() : d_fri_evals[l].as<fe>();
+                k_gather_fri_rows<<<(th + 127) / 128, 128, 0, stream>>>(e, j.domain, dpos, j.np, drows);
+            }
+            check_launch();
+            if (j.nflat) {
+                k_gather_digests<<<(unsigned)((j.nflat * 2 + 127) / 128), 128, 0, stream>>>(j.heap, (const uint64_t*)(base + j.o_idx), (uint32_t)j.nflat,
+                                                                                        (uint32_t*)(drows + (size_t)j.np * j.width));
+                check_launch();
+            }
+        }
+        std::vector<uint8_t> host(out_bytes);
+        d2h(host.data(), base + o_out0, out_bytes);
+        for (size_t q = 0; q < reqs.size(); q++) {
+            const Job& j = jobs[q];
+            const uint8_t* h = host.data() + j.o_out;
+            const size_t rb = (size_t)j.np * j.width * 16;
+            reqs[q].rows->assign(h, h + rb);
+            *reqs[q].paths = batch_proof_bytes(j.depth, j.plan, h + rb);
+        }
+    }
+
     // ==========================================================================================================
     // Prover::prove: the whole pipeline with the channel on the host  
     // sharded = true: `cols` / `d_trace_in` hold only this rank's w/G columns and the proof is produced cooperatively by all
@@ -1134,16 +1199,24 @@ struct zkb_ctx {
         ts.n_positions = parts.n_unique;
         for (size_t i = 0; i < positions.size() && i < 256; i++) ts.positions[i] = positions[i];
         {   // FriProver::build_proof, TraceLde::query, ConstraintCommitment::query
-            std::vector<uint32_t> pos = positions;
+            std::vector<std::vector<uint32_t>> fpos(fri_layers);
             uint64_t dom = air.lde_size();
             parts.fri_rows.resize(fri_layers); parts.fri_paths.resize(fri_layers);
             for (uint32_t l = 0; l < fri_layers; l++) {
-                pos = fold_positions(pos, dom, 16);
-                query(2 + l, pos, parts.fri_rows[l], parts.fri_paths[l]);
+                fpos[l] = fold_positions(l ? fpos[l - 1] : positions, dom, 16);
                 dom /= 16;
             }
-            query(0, positions, parts.trace_rows, parts.trace_paths);
-            query(1, positions, parts.comp_rows, parts.comp_paths);
+            if (!mg_active) {
+                std::vector<QueryReq> reqs;
+                for (uint32_t l = 0; l < fri_layers; l++) reqs.push_back({2 + l, &fpos[l], &parts.fri_rows[l], &parts.fri_paths[l]});
+                reqs.push_back({0, &positions, &parts.trace_rows, &parts.trace_paths});
+                reqs.push_back({1, &positions, &parts.comp_rows, &parts.comp_paths});
+                query_all(reqs);
+            } else {
+                for (uint32_t l = 0; l < fri_layers; l++) query(2 + l, fpos[l], parts.fri_rows[l], parts.fri_paths[l]);
+                query(0, positions, parts.trace_rows, parts.trace_paths);
+                query(1, positions, parts.comp_rows, parts.comp_paths);
+            }
         }
         t_end(TS_QUERY);
         t_end(TS_TOTAL);
