@@ -85,7 +85,12 @@ template <int V> __device__ __forceinline__ fe mulv(const fe& a, const fe& b) {
     return reduce_C(w);
 }
 
+#ifndef UNITS
 #define UNITS 8
+#endif
+#ifndef BPS
+#define BPS 3
+#endif
 template <int V>
 __global__ void __launch_bounds__(256) k(fe* io, const fe* tw, int iters) {
     fe x[UNITS], y[UNITS];
@@ -107,7 +112,7 @@ __global__ void __launch_bounds__(256) k(fe* io, const fe* tw, int iters) {
 }
 
 template <int V> void run(const char* name, fe* io, fe* tw, unsigned long long* ref, bool check) {
-    const int blocks = 148 * 3, threads = 256, iters = 2000;
+    const int blocks = 148 * BPS, threads = 256, iters = 2000;
     cudaMemset(io, 0x5a, (size_t)blocks * threads * 2 * UNITS * 16);
     // make inputs canonical-ish: clear the top bit of every element
     k<V><<<blocks, threads>>>(io, tw, 4);
@@ -127,7 +132,7 @@ template <int V> void run(const char* name, fe* io, fe* tw, unsigned long long* 
 
 int main() {
     fe *io, *tw;
-    cudaMalloc(&io, (size_t)148 * 3 * 256 * 2 * UNITS * 16);
+    cudaMalloc(&io, (size_t)148 * BPS * 256 * 2 * UNITS * 16);
     cudaMalloc(&tw, 32 * 16);
     unsigned long long host_tw[64];
     for (int i = 0; i < 64; i++) host_tw[i] = 0x9E3779B97F4A7C15ULL * (i + 1) >> (i & 1);
