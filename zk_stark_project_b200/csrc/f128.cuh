@@ -264,16 +264,25 @@ __device__ __forceinline__ fe fe_pow_u64(fe b, uint64_t e) {
     while (e) { if (e & 1) r = fe_mul(r, b); b = fe_sqr(b); e >>= 1; }
     return r;
 }
-// a^(p-2); inv(0) = 0 as in winter-math
+// a^(p-2); inv(0) = 0 as in winter-math.  p - 2 = 0xFFFFFFFF_FFFFFFFF_FFFFD2FF_FFFFFFFF: 80 ones, 1101001011111111, 32 ones.
+// Addition chain over e_k = a^(2^k - 1): 127 squarings + 12 multiplications (square-and-multiply needs 127 + 121).
+__device__ __forceinline__ fe fe_sqr_n(fe x, int k) {
+    for (int i = 0; i < k; i++) x = fe_sqr(x);
+    return x;
+}
 __device__ __noinline__ fe fe_inv(const fe& a) {
-    // p - 2 = 0xFFFFFFFF_FFFFFFFF_FFFFD2FF_FFFFFFFF
-    const uint32_t e[4] = {0xFFFFFFFFu, 0xFFFFD2FFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-    fe r = fe_one();
-    for (int i = 127; i >= 0; i--) {
-        r = fe_sqr(r);
-        if ((e[i >> 5] >> (i & 31)) & 1) r = fe_mul(r, a);
-    }
-    return r;
+    const fe e2 = fe_mul(fe_sqr(a), a);
+    const fe e4 = fe_mul(fe_sqr_n(e2, 2), e2);
+    const fe e8 = fe_mul(fe_sqr_n(e4, 4), e4);
+    const fe e16 = fe_mul(fe_sqr_n(e8, 8), e8);
+    const fe e32 = fe_mul(fe_sqr_n(e16, 16), e16);
+    const fe e64 = fe_mul(fe_sqr_n(e32, 32), e32);
+    fe r = fe_mul(fe_sqr_n(e64, 16), e16);   // bits 127..48
+    r = fe_mul(fe_sqr_n(r, 2), e2);          // 11
+    r = fe_mul(fe_sqr_n(r, 2), a);           // 01
+    r = fe_mul(fe_sqr_n(r, 3), a);           // 001
+    r = fe_mul(fe_sqr_n(r, 9), e8);          // 0 11111111
+    return fe_mul(fe_sqr_n(r, 32), e32);     // 32 ones
 }
 
 }  // namespace zkb

@@ -519,10 +519,18 @@ __global__ void __launch_bounds__(256) k_ood_partial(const fe* __restrict__ poly
                                                       fe* __restrict__ part_z, fe* __restrict__ part_zg) {
     // z^(R c), (zg)^(R c) of each row chunk in the block: one thread per chunk raises z^R to the chunk index (<= 2 log2(n/R)
     // multiplications, against 2 R wq for the chunk itself) instead of the host tabulating n/R powers per proof
+    // The chunk itself is a dot product with z^0..z^(R-1) (tabulated once per block, R <= 64) accumulated as exact 288-bit
+    // integers and reduced once: no dependent Horner chain, one reduction per chunk instead of one per coefficient.
     __shared__ uint4 zs[2][256];
+    __shared__ uint4 zp[2][64];
     const uint32_t j = threadIdx.x & ((1u << log_wq) - 1u), sub = threadIdx.x >> log_wq;
     const uint32_t c = blockIdx.x * (256u >> log_wq) + sub;
     const uint32_t m0 = c * R;
+    if (threadIdx.x < R) {
+        const fe a = fe_pow_u64(z, threadIdx.x), b = fe_pow_u64(zg, threadIdx.x);
+        zp[0][threadIdx.x] = make_uint4(a.x[0], a.x[1], a.x[2], a.x[3]);
+        zp[1][threadIdx.x] = make_uint4(b.x[0], b.x[1], b.x[2], b.x[3]);
+    }
     if (j == 0 && m0 < n) {
         const fe a = fe_pow_u64(zR, c), b = fe_pow_u64(zgR, c);
         zs[0][sub] = make_uint4(a.x[0], a.x[1], a.x[2], a.x[3]);
@@ -531,17 +539,20 @@ __global__ void __launch_bounds__(256) k_ood_partial(const fe* __restrict__ poly
     __syncthreads();
     if (j >= w || m0 >= n) return;
     const uint32_t m1 = min(n, m0 + R);
-    fe a = fe_zero(), b = fe_zero();
-    for (uint32_t m = m1; m-- > m0;) {
-        fe v = fe_load(polys + (size_t)m * w + j);
-        a = fe_add(fe_mul(a, z), v);
-        b = fe_add(fe_mul(b, zg), v);
+    acc288 az, ag; acc288_zero(az); acc288_zero(ag);
+    for (uint32_t m = m0; m < m1; m++) {
+        const fe v = fe_load(polys + (size_t)m * w + j);
+        fe pz, pg;
+        { const uint4 t = zp[0][m - m0]; pz.x[0] = t.x; pz.x[1] = t.y; pz.x[2] = t.z; pz.x[3] = t.w; }
+        { const uint4 t = zp[1][m - m0]; pg.x[0] = t.x; pg.x[1] = t.y; pg.x[2] = t.z; pg.x[3] = t.w; }
+        acc288_mad(az, v, pz);
+        acc288_mad(ag, v, pg);
     }
     fe pa, pb;
     { const uint4 t = zs[0][sub]; pa.x[0] = t.x; pa.x[1] = t.y; pa.x[2] = t.z; pa.x[3] = t.w; }
     { const uint4 t = zs[1][sub]; pb.x[0] = t.x; pb.x[1] = t.y; pb.x[2] = t.z; pb.x[3] = t.w; }
-    fe_store(part_z + (size_t)c * w + j, fe_mul(a, pa));
-    fe_store(part_zg + (size_t)c * w + j, fe_mul(b, pb));
+    fe_store(part_z + (size_t)c * w + j, fe_mul(acc288_reduce(az), pa));
+    fe_store(part_zg + (size_t)c * w + j, fe_mul(acc288_reduce(ag), pb));
 }
 // out[j] = sum_c part[c][j]; block = 32 columns x 32 chunk lanes, tree-reduced in shared memory
 __global__ void __launch_bounds__(1024) k_col_sum(const fe* __restrict__ part, uint32_t nchunks, uint32_t w, fe* __restrict__ out) {
