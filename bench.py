@@ -475,10 +475,10 @@ def main():
                          # dram__bytes_read+write summed over the K1+K2 launches of one proof (transpose, 2 interpolation passes, 2 LDE
                          # passes; ncu, profiles/r1_ncu_k1k2_dram_traffic.csv): 2.8x the algorithmic bytes because n = 2^16 needs two
                          # passes through HBM per transform (a shared-memory tile holds 2^8 rows x 16 columns)
-                         "traffic": 13.566e9 if args.workload == "training_2p16" and not sharded else None, "peak_source": peak_src,
+                         "traffic": 13.580e9 if args.workload == "training_2p16" and not sharded else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_proof": alg["lde"], "kernel_ms_per_proof": lde_ms,
-                         "note": "bound by the FMA-heavy (IMAD) pipe, not HBM: a radix-2 f128 butterfly is ~105 SASS integer instructions "
-                                 "per 32 bytes moved; ncu: sm__pipe_fmaheavy_cycles_active 73%, DRAM 9-16% (profiles/r1_ncu_ntt_lde_v1_radix8_regs.txt)"},
+                         "note": "bound by integer issue (FMA-heavy + ALU pipes), not HBM: a radix-2 f128 butterfly is ~100 SASS integer instructions "
+                                 "per 32 bytes moved; ncu: sm__pipe_fmaheavy_cycles_active 75%, ALU 57%, DRAM 9-17% (profiles/r1_ncu_ntt_lde_final.txt)"},
             # what actually bounds K1/K2: integer issue.  Peak = register-resident radix-2 f128 butterflies/s measured on this pool's
             # B200 by tools/mul_variants.cu (no memory traffic at all; profiles/r1_mul_variants_butterfly_peak.txt)
             "compute_roofline": {"unit": "G butterflies/s", "peak": 203.5,
