@@ -1,6 +1,7 @@
 //! Byte-parity harness: `winterfell::Prover::prove` (the reference's stock CPU path) against `zkb_prove` on the SAME trace.
 //!
-//! NOT COMPILED IN THIS REPOSITORY (no Rust toolchain in the build image).  For every case it
+//! NOT COMPILED IN THIS REPOSITORY (no Rust toolchain in the build image).  Needs the two `impl GpuProve for ...` blocks of
+//! INTEGRATION.md §2 in the reference checkout (the orphan rule keeps them out of this crate).  For every case it
 //!   1. builds the reference prover exactly as tests/integration_tests.rs:14-56 does (deterministic inputs; the trace itself
 //!      contains `thread_rng` masks, src/training/prover.rs:119-121, so the trace is built ONCE and handed to both provers),
 //!   2. proves with Winterfell and with the B200 library,
