@@ -105,6 +105,15 @@ int32_t zkb_prove(zkb_ctx* ctx, const zkb_air_desc* air, const uint8_t* const* c
 /* same, with the column-major trace [w][n] already resident in device memory */
 int32_t zkb_prove_device(zkb_ctx* ctx, const zkb_air_desc* air, const void* d_trace_colmajor, uint64_t force_nonce,
                          uint8_t** proof_out, uint64_t* proof_len, zkb_transcript* transcript);
+/*
+ * A batch of independent proofs (BASELINE configs[3]: the reference proves its devices one after the other, src/main.rs:160,379):
+ * proof i runs on lanes[i % n_lanes]; every lane is a zkb_ctx of its own (device + stream + buffers) driven by its own host thread
+ * inside the call, so H2D copies, kernels and Fiat-Shamir round trips of different proofs overlap.  Lanes may sit on different
+ * devices.  proofs_out[i] / lens_out[i] as in zkb_prove (release each with zkb_free); on failure the first failing proof's status is
+ * returned, its message is in that lane's zkb_last_error, and the outputs of proofs that did not complete are NULL / 0.
+ */
+int32_t zkb_prove_batch(zkb_ctx* const* lanes, uint32_t n_lanes, const zkb_air_desc* const* airs, const uint8_t* const* const* cols,
+                        uint32_t count, uint8_t** proofs_out, uint64_t* lens_out);
 void zkb_free(void* p);
 
 /* ---- staged surface: the three associated types + the stages inside Prover::prove ------------------------

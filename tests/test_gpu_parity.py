@@ -331,6 +331,7 @@ def test_prove_batch_single_rank(gpu_ctx, oracle):
         jobs.append((p, p.build_trace()))
     proofs = M.prove_batch(jobs, gpu_ctx)
     assert len(proofs) == 4 and len({M.digest(p) for p in proofs}) == 4
+    assert M.prove_batch(jobs, gpu_ctx, lanes=[L.Context(0)]) == proofs  # same through zkb_prove_batch with two lanes
     for (p, tr), proof in zip(jobs, proofs):
         assert Z.verify(proof, p.describe(tr))
         assert proof == oracle.prove(p.describe(tr), tr.to_bytes())[0]
@@ -410,3 +411,27 @@ def test_boundary_polynomial_path_forced():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k", sel, "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_native_prove_batch(gpu_ctx, oracle):
+    """zkb_prove_batch (BASELINE configs[3]): a mixed batch over three lanes returns, in order, exactly the proofs the one-shot
+    call produces; a bad job fails the call with its status and leaves the other jobs' proofs intact."""
+    lanes = [gpu_ctx, L.Context(0), L.Context(0)]
+    jobs = []
+    for i in range(7):
+        p = T.mimc_prover(1 + i, 128, T.options(blowup=8, grinding=4)) if i % 2 else T.training_prover(1 + i // 2, T.options(grinding=4))
+        tr = p.build_trace()
+        jobs.append((p.describe(tr), np.ascontiguousarray(tr.data)))
+    proofs = L.prove_batch(lanes, [a for a, _ in jobs], [d.ctypes.data for _, d in jobs])
+    for (air, data), proof in zip(jobs, proofs):
+        single, _ = gpu_ctx.prove_host(air, data.ctypes.data)
+        assert proof == single
+        oracle.verify(air, proof)
+    assert L.prove_batch(lanes, [], []) == []
+    bad = dict(jobs[1][0], options=dict(jobs[1][0]["options"], blowup=3))
+    with pytest.raises(L.ZkbError) as e:
+        L.prove_batch(lanes, [jobs[0][0], bad, jobs[2][0]], [jobs[0][1].ctypes.data, jobs[1][1].ctypes.data, jobs[2][1].ctypes.data])
+    assert e.value.status == -1  # ZKB_ERR_INVALID
+    # the lanes are still usable afterwards
+    again, _ = lanes[1].prove_host(jobs[0][0], jobs[0][1].ctypes.data)
+    assert again == proofs[0]

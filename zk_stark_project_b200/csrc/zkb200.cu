@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <functional>
 #include <map>
+#include <thread>
 #include <tuple>
 #include <memory>
 #include "kernels.cuh"
@@ -1292,6 +1293,28 @@ int32_t zkb_prove_device(zkb_ctx* ctx, const zkb_air_desc* air, const void* d_tr
         if (proof_len) *proof_len = b.size();
         if (proof_out) *proof_out = dup_bytes(b);
     });
+}
+
+int32_t zkb_prove_batch(zkb_ctx* const* lanes, uint32_t n_lanes, const zkb_air_desc* const* airs, const uint8_t* const* const* cols,
+                        uint32_t count, uint8_t** proofs_out, uint64_t* lens_out) {
+    if (!lanes || n_lanes == 0 || !proofs_out || !lens_out || (count && (!airs || !cols))) { g_last_error = "zkb_prove_batch: null argument"; return ZKB_ERR_INVALID; }
+    for (uint32_t l = 0; l < n_lanes; l++) if (!lanes[l]) { g_last_error = "zkb_prove_batch: null lane"; return ZKB_ERR_INVALID; }
+    for (uint32_t i = 0; i < count; i++) { proofs_out[i] = nullptr; lens_out[i] = 0; }
+    std::vector<int32_t> rc(n_lanes, ZKB_OK);
+    std::vector<uint32_t> failed(n_lanes, UINT32_MAX);
+    auto work = [&](uint32_t l) {
+        for (uint32_t i = l; i < count; i += n_lanes) {
+            const int32_t r = zkb_prove(lanes[l], airs[i], cols[i], 0, &proofs_out[i], &lens_out[i], nullptr);
+            if (r != ZKB_OK) { rc[l] = r; failed[l] = i; return; }   // the lane stops at its first failure
+        }
+    };
+    std::vector<std::thread> threads;
+    for (uint32_t l = 1; l < n_lanes && l < count; l++) threads.emplace_back(work, l);
+    work(0);
+    for (auto& t : threads) t.join();
+    uint32_t first = UINT32_MAX; int32_t out = ZKB_OK;
+    for (uint32_t l = 0; l < n_lanes; l++) if (rc[l] != ZKB_OK && failed[l] < first) { first = failed[l]; out = rc[l]; }
+    return out;
 }
 
 int32_t zkb_begin(zkb_ctx* ctx, const zkb_air_desc* air) { return guarded(ctx, [&] { ctx->begin(air); }); }

@@ -77,7 +77,7 @@ EXPORTS = [
     "zkb_host_free", "zkb_prove", "zkb_prove_device", "zkb_free", "zkb_begin", "zkb_trace_commit", "zkb_trace_commit_device",
     "zkb_trace_read_frame", "zkb_trace_polys_read", "zkb_constraints_eval", "zkb_constraints_commit", "zkb_ood_eval",
     "zkb_deep_compose", "zkb_fri_num_layers", "zkb_fri_commit_layer", "zkb_fri_fold", "zkb_fri_remainder", "zkb_grind",
-    "zkb_query", "zkb_mg_unique_id", "zkb_mg_init", "zkb_mg_prove", "zkb_mg_prove_device", "zkb_mimc_trace", "zkb_mimc_trace_device", "zkb_training_trace_device", "zkb_download", "zkb_blake3_host", "zkb_mimc_cipher_batch", "zkb_mimc_hash_matrix_batch", "zkb_upload_trace", "zkb_test_field", "zkb_test_hash_elements",
+    "zkb_query", "zkb_mg_unique_id", "zkb_mg_init", "zkb_mg_prove", "zkb_mg_prove_device", "zkb_prove_batch", "zkb_mimc_trace", "zkb_mimc_trace_device", "zkb_training_trace_device", "zkb_download", "zkb_blake3_host", "zkb_mimc_cipher_batch", "zkb_mimc_hash_matrix_batch", "zkb_upload_trace", "zkb_test_field", "zkb_test_hash_elements",
     "zkb_test_merkle_root", "zkb_test_lde",
 ]
 
@@ -248,6 +248,30 @@ def blake3_host(data):
     if rc != 0:
         raise ZkbError(rc, "zkb_blake3_host failed")
     return out.raw
+
+
+def prove_batch(lanes, airs, trace_ptrs):
+    """zkb_prove_batch: proof i (AIR description airs[i], column-major host trace at trace_ptrs[i]) runs on lanes[i % len(lanes)];
+    the host threads live inside the library.  Returns the proofs in order."""
+    count = len(airs)
+    descs = [Context.prepare(a) for a in airs]
+    lane_arr = (C.c_void_p * len(lanes))(*[l.handle for l in lanes])
+    air_arr = (C.POINTER(AirDesc) * max(count, 1))(*[C.pointer(d) for d in descs])
+    col_arrays = [lanes[0]._col_ptrs(p, d.trace_width, d.trace_len) for p, d in zip(trace_ptrs, descs)]
+    cols_arr = (C.c_void_p * max(count, 1))(*[C.cast(c, C.c_void_p) for c in col_arrays])
+    outs = (C.c_void_p * max(count, 1))()
+    lens = (C.c_uint64 * max(count, 1))()
+    lib = lanes[0].lib
+    rc = lib.zkb_prove_batch(lane_arr, C.c_uint32(len(lanes)), air_arr, cols_arr, C.c_uint32(count), outs, lens)
+    proofs = []
+    for i in range(count):
+        proofs.append(C.string_at(outs[i], lens[i]) if outs[i] else None)
+        if outs[i]:
+            lib.zkb_free(C.c_void_p(outs[i]))
+    if rc != 0:
+        msgs = [lib.zkb_last_error(l.handle).decode() for l in lanes]
+        raise ZkbError(rc, "; ".join(m for m in msgs if m))
+    return proofs
 
 
 def mimc_cipher_batch(ctx, xs, rcs, zs):

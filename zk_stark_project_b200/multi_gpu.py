@@ -37,16 +37,23 @@ def max_over_ranks(value, dist=None, device=None):
     return float(t[0])
 
 
-def prove_batch(provers_and_traces, ctx, rank=0, world_size=1, dist=None):
-    """Config 4: a batch of independent proofs, proof i on rank i % world_size; returns all proofs on every rank."""
+def prove_batch(provers_and_traces, ctx, rank=0, world_size=1, dist=None, lanes=None):
+    """Config 4: a batch of independent proofs, proof i on rank i % world_size; returns all proofs on every rank.
+    `lanes`: extra zkb contexts on this rank's device — this rank's share then goes through zkb_prove_batch, which keeps
+    len(lanes) + 1 proofs in flight (host threads inside the library)."""
     import numpy as np
-    mine = {}
-    for i in shard_proofs(len(provers_and_traces), world_size, rank):
+    from . import lib as L
+    idx = list(shard_proofs(len(provers_and_traces), world_size, rank))
+    airs, datas = [], []
+    for i in idx:
         prover, trace = provers_and_traces[i]
-        data = np.ascontiguousarray(trace.data)
-        proof, _ = ctx.prove_host(prover.describe(trace), data.ctypes.data)
-        mine[i] = proof
-    return gather_proofs(mine, len(provers_and_traces), dist)
+        airs.append(prover.describe(trace))
+        datas.append(np.ascontiguousarray(trace.data))
+    if lanes:
+        proofs = L.prove_batch([ctx] + list(lanes), airs, [d.ctypes.data for d in datas])
+    else:
+        proofs = [ctx.prove_host(a, d.ctypes.data)[0] for a, d in zip(airs, datas)]
+    return gather_proofs(dict(zip(idx, proofs)), len(provers_and_traces), dist)
 
 
 def digest(proof):
