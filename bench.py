@@ -279,7 +279,7 @@ def main():
     ap.add_argument("--workload", default="training_2p16", choices=sorted(WORKLOADS) + ["mimc_helpers"])
     ap.add_argument("--impl", default="zkb200", choices=["zkb200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle timing at N=1")
-    ap.add_argument("--inflight", type=int, default=2,
+    ap.add_argument("--inflight", type=int, default=4,
                     help="independent proofs in flight per GPU in the throughput arms (one zkb_ctx + CUDA stream + host thread each); "
                          "single-proof latency is always measured too and reported as prove_ms")
     ap.add_argument("--sharded", action="store_true",
