@@ -3,7 +3,8 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl zkb200|reference]
 
-A step is one complete proof (`Prover::prove`, /root/reference src/main.rs:228) of a seeded synthetic trace.
+A step is `--inflight` (default 4) complete proofs per GPU (`Prover::prove`, /root/reference src/main.rs:228), each of its own
+seeded synthetic trace, kept in flight on separate contexts; `prove_ms` is the latency of one proof proved alone.
 `value` times it with the trace already resident in HBM, `e2e` through the C ABI with pinned HOST columns
 (H2D of the trace and D2H of the proof inside the timed region).  Multi-GPU runs one independent proof stream
 per rank (weak scaling, no collective on the data path).  `--impl reference` times the CPU oracle — the
