@@ -8,10 +8,14 @@
 // All four must produce the same field elements (checksum printed).
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/eval_variants tools/eval_variants.cu && ./tools/eval_variants
 #include <cstdio>
-#include "../zk_stark_project_b200/csrc/f128.cuh"
+#include "reduce_variants.cuh"
 using namespace zkb;
 
 #define COLS 8
+// R = 0: shipped mad-chain folds; 1: variant B; 2: variant C (fewer IMADs, more ALU work)
+template <int R> __device__ __forceinline__ fe red(const uint32_t w[8]) { return R == 0 ? fe_reduce256(w) : (R == 1 ? reduce_B(w) : reduce_C(w)); }
+template <int R> __device__ __forceinline__ fe mulr(const fe& a, const fe& b) { uint32_t w[8]; mul_wide(a, b, w); return red<R>(w); }
+template <int R> __device__ __forceinline__ fe sqrr(const fe& a) { uint32_t w[8]; sqr_wide(a, w); return red<R>(w); }
 template <int V>
 __global__ void __launch_bounds__(128) k(fe* io, const fe* coef, int iters) {
     fe cur[COLS], nxt[COLS];
@@ -27,8 +31,9 @@ __global__ void __launch_bounds__(128) k(fe* io, const fe* coef, int iters) {
         for (int u = 0; u < COLS; u++) {
             const fe a1 = fe_add(cur[u], rc);
             fe a2, a4;
-            if (V & 1) { a2 = fe_sqr(a1); a4 = fe_sqr(a2); } else { a2 = fe_mul(a1, a1); a4 = fe_mul(a2, a2); }
-            const fe a6 = fe_mul(a4, a2), a7 = fe_mul(a6, a1);
+            constexpr int R = V >> 2;
+            if (V & 1) { a2 = sqrr<R>(a1); a4 = sqrr<R>(a2); } else { a2 = mulr<R>(a1, a1); a4 = mulr<R>(a2, a2); }
+            const fe a6 = mulr<R>(a4, a2), a7 = mulr<R>(a6, a1);
             const fe ev = fe_sub(nxt[u], a7);
             const fe cf = fe_ldg(coef + u);
             if (V & 2) acc288_mad(acc, cf, ev); else tt = fe_add(tt, fe_mul(cf, ev));
@@ -70,5 +75,7 @@ int main() {
     run<1>("1 dedicated squaring", io, coef, ref, true);
     run<2>("2 lazy 288-bit accumulation", io, coef, ref, true);
     run<3>("3 both", io, coef, ref, true);
+    run<7>("7 both + reduction B (shift/funnel)", io, coef, ref, true);
+    run<11>("11 both + reduction C (limb shift + c1)", io, coef, ref, true);
     return 0;
 }
