@@ -85,6 +85,9 @@ typedef struct {
 /* ---- context ------------------------------------------------------------------------------------ */
 /* stream: a cudaStream_t (or NULL for the default stream) the caller wants all work issued on */
 int32_t zkb_ctx_create(int32_t device, void* stream, zkb_ctx** out);
+/* same, on a private non-blocking stream created and destroyed with the context: what the lanes of zkb_prove_batch should be
+ * (contexts that share the default stream are correct but run one after the other) */
+int32_t zkb_ctx_create_lane(int32_t device, zkb_ctx** out);
 void zkb_ctx_destroy(zkb_ctx* ctx);
 const char* zkb_last_error(const zkb_ctx* ctx);
 /* number of kernels the context has launched so far (evidence for bench.py's gpu_launches) */
@@ -108,8 +111,8 @@ int32_t zkb_prove_device(zkb_ctx* ctx, const zkb_air_desc* air, const void* d_tr
 /*
  * A batch of independent proofs (BASELINE configs[3]: the reference proves its devices one after the other, src/main.rs:160,379):
  * proof i runs on lanes[i % n_lanes]; every lane is a zkb_ctx of its own (device + stream + buffers) driven by its own host thread
- * inside the call, so H2D copies, kernels and Fiat-Shamir round trips of different proofs overlap.  Lanes may sit on different
- * devices.  proofs_out[i] / lens_out[i] as in zkb_prove (release each with zkb_free); on failure the first failing proof's status is
+ * inside the call, so H2D copies, kernels and Fiat-Shamir round trips of different proofs overlap (create the lanes with
+ * zkb_ctx_create_lane or on distinct streams).  Lanes may sit on different devices.  proofs_out[i] / lens_out[i] as in zkb_prove (release each with zkb_free); on failure the first failing proof's status is
  * returned, its message is in that lane's zkb_last_error, and the outputs of proofs that did not complete are NULL / 0.
  */
 int32_t zkb_prove_batch(zkb_ctx* const* lanes, uint32_t n_lanes, const zkb_air_desc* const* airs, const uint8_t* const* const* cols,

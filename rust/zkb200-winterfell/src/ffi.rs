@@ -54,6 +54,7 @@ pub const ZKB_AIR_ID_MIMC: u32 = 3;
 
 extern "C" {
     pub fn zkb_ctx_create(device: i32, stream: *mut c_void, out: *mut *mut zkb_ctx) -> i32;
+    pub fn zkb_ctx_create_lane(device: i32, out: *mut *mut zkb_ctx) -> i32;
     pub fn zkb_ctx_destroy(ctx: *mut zkb_ctx);
     pub fn zkb_last_error(ctx: *const zkb_ctx) -> *const c_char;
     pub fn zkb_free(p: *mut c_void);

@@ -331,7 +331,7 @@ def test_prove_batch_single_rank(gpu_ctx, oracle):
         jobs.append((p, p.build_trace()))
     proofs = M.prove_batch(jobs, gpu_ctx)
     assert len(proofs) == 4 and len({M.digest(p) for p in proofs}) == 4
-    assert M.prove_batch(jobs, gpu_ctx, lanes=[L.Context(0)]) == proofs  # same through zkb_prove_batch with two lanes
+    assert M.prove_batch(jobs, gpu_ctx, lanes=[L.Context(0, own_stream=True)]) == proofs  # same through zkb_prove_batch with two lanes
     for (p, tr), proof in zip(jobs, proofs):
         assert Z.verify(proof, p.describe(tr))
         assert proof == oracle.prove(p.describe(tr), tr.to_bytes())[0]
@@ -416,7 +416,7 @@ def test_boundary_polynomial_path_forced():
 def test_native_prove_batch(gpu_ctx, oracle):
     """zkb_prove_batch (BASELINE configs[3]): a mixed batch over three lanes returns, in order, exactly the proofs the one-shot
     call produces; a bad job fails the call with its status and leaves the other jobs' proofs intact."""
-    lanes = [gpu_ctx, L.Context(0), L.Context(0)]
+    lanes = [gpu_ctx, L.Context(0, own_stream=True), L.Context(0, own_stream=True)]
     jobs = []
     for i in range(7):
         p = T.mimc_prover(1 + i, 128, T.options(blowup=8, grinding=4)) if i % 2 else T.training_prover(1 + i // 2, T.options(grinding=4))

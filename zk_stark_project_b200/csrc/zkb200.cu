@@ -108,6 +108,7 @@ struct zkb_ctx {
     uint64_t per_cache_n = 0, per_cache_ce = 0;
     cudaEvent_t ev_group[17];          // per column group: "H2D of this group has landed"
     cudaStream_t copy_stream = nullptr;  // trace ingest overlaps the NTTs of earlier column groups
+    bool owns_stream = false;            // zkb_ctx_create_lane: `stream` was created by the context
     cudaStream_t xchg_stream = nullptr;  // sharded proofs: the NVLink all-to-all of finished coset batches overlaps the LDE of the next
     bool ev_ok = false;
 
@@ -185,6 +186,7 @@ struct zkb_ctx {
         for (auto& kv : tw_cache) kv.second.release();
         if (ev_ok) { for (auto& pr : tev) for (auto& x : pr) cudaEventDestroy(x); for (auto& x : ev_group) cudaEventDestroy(x); cudaStreamDestroy(copy_stream); cudaStreamDestroy(xchg_stream); }
         if (h_stage) cudaFreeHost(h_stage);
+        if (owns_stream && stream) { cudaStreamDestroy(stream); stream = nullptr; }
     }
 
     void h2d(void* dst, const void* src, size_t bytes) { CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream)); }
@@ -1258,6 +1260,21 @@ int32_t zkb_ctx_create(int32_t device, void* stream, zkb_ctx** out) {
     } catch (const InvalidArg& e) { g_last_error = e.what(); delete c; return ZKB_ERR_INVALID; }
     catch (const std::exception& e) { g_last_error = e.what(); delete c; return ZKB_ERR_CUDA; }
     *out = c;
+    return ZKB_OK;
+}
+int32_t zkb_ctx_create_lane(int32_t device, zkb_ctx** out) {
+    if (!out) { g_last_error = "null output pointer"; return ZKB_ERR_INVALID; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_last_error = "no CUDA device available"; return ZKB_ERR_CUDA; }
+    if (device < 0 || device >= ndev) { g_last_error = "device index out of range"; return ZKB_ERR_INVALID; }
+    cudaStream_t st = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+        g_last_error = "cannot create a stream for the lane"; return ZKB_ERR_CUDA;
+    }
+    const int32_t rc = zkb_ctx_create(device, st, out);
+    if (rc != ZKB_OK) { cudaStreamDestroy(st); return rc; }
+    (*out)->owns_stream = true;
     return ZKB_OK;
 }
 void zkb_ctx_destroy(zkb_ctx* ctx) { if (ctx) { ctx->destroy(); delete ctx; } }

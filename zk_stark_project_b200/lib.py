@@ -73,7 +73,7 @@ def load():
 
 # every symbol include/zkb200.h declares
 EXPORTS = [
-    "zkb_ctx_create", "zkb_ctx_destroy", "zkb_last_error", "zkb_kernel_launches", "zkb_last_stage_times", "zkb_host_alloc",
+    "zkb_ctx_create", "zkb_ctx_create_lane", "zkb_ctx_destroy", "zkb_last_error", "zkb_kernel_launches", "zkb_last_stage_times", "zkb_host_alloc",
     "zkb_host_free", "zkb_prove", "zkb_prove_device", "zkb_free", "zkb_begin", "zkb_trace_commit", "zkb_trace_commit_device",
     "zkb_trace_read_frame", "zkb_trace_polys_read", "zkb_constraints_eval", "zkb_constraints_commit", "zkb_ood_eval",
     "zkb_deep_compose", "zkb_fri_num_layers", "zkb_fri_commit_layer", "zkb_fri_fold", "zkb_fri_remainder", "zkb_grind",
@@ -124,10 +124,14 @@ def make_desc(air):
 class Context:
     """One zkb_ctx: a device + stream binding that owns all device memory of the proofs run through it."""
 
-    def __init__(self, device=0, stream=None):
+    def __init__(self, device=0, stream=None, own_stream=False):
+        """stream: a cudaStream_t value (None = default stream); own_stream=True: a private stream (zkb_ctx_create_lane)."""
         self.lib = load()
         self.handle = C.c_void_p()
-        rc = self.lib.zkb_ctx_create(C.c_int32(device), C.c_void_p(stream or 0), C.byref(self.handle))
+        if own_stream:
+            rc = self.lib.zkb_ctx_create_lane(C.c_int32(device), C.byref(self.handle))
+        else:
+            rc = self.lib.zkb_ctx_create(C.c_int32(device), C.c_void_p(stream or 0), C.byref(self.handle))
         if rc != 0:
             raise ZkbError(rc, self.lib.zkb_last_error(None).decode())
         self.device = device
