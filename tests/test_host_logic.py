@@ -138,3 +138,28 @@ def test_invalid_inputs_panic():
         Z.TrainingUpdateProver(T.options(), [[0] * 9] * 6, [0] * 6, [[0] * 9] * 6, [0] * 6, [[0] * 9], [[0] * 9], [[0] * 6], 1, 1, 2)
     with pytest.raises(ValueError):
         Z.MimcProver(T.options(), [1], 100)
+
+
+def test_device_field_constants_in_source():
+    """Constants and the inversion addition chain hard-wired in csrc/f128.cuh, re-derived here (the GPU KAT checks the code;
+    this guards the numbers against an edit on a machine without a GPU)."""
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "zk_stark_project_b200", "csrc", "f128.cuh")).read()
+    c = (1 << 128) % P
+    assert c == 45 * 2**40 - 1
+    assert f"#define ZKB_C0 0x{c & 0xFFFFFFFF:08X}u" in src and f"#define ZKB_C1 0x{c >> 32:08X}u" in src
+    k = (1 << 256) % P  # weight of the accumulator's ninth limb
+    assert k == c * c and k < 2**92
+    m = re.search(r"k0 = (0x[0-9A-Fa-f]+)u, k1 = (0x[0-9A-Fa-f]+)u, k2 = (0x[0-9A-Fa-f]+)u", src)
+    assert m and [int(x, 16) for x in m.groups()] == [(k >> (32 * i)) & 0xFFFFFFFF for i in range(3)]
+    # fe_inv: e_k = a^(2^k - 1); the chain in the source is (shift, multiply-by) pairs after e64
+    steps = re.findall(r"r = fe_mul\(fe_sqr_n\((\w+), (\d+)\), (\w+)\);|return fe_mul\(fe_sqr_n\(r, (\d+)\), (\w+)\);", src)
+    e = {"a": 1, "e2": 3, "e4": 15, "e8": 255, "e16": 2**16 - 1, "e32": 2**32 - 1, "e64": 2**64 - 1}
+    exp = None
+    for base, sh, mul, sh_last, mul_last in steps:
+        if sh_last:
+            exp = (exp << int(sh_last)) + e[mul_last]
+        else:
+            exp = ((e[base] if base != "r" else exp) << int(sh)) + e[mul]
+    assert exp == P - 2
