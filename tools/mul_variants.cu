@@ -7,6 +7,18 @@
 #include "reduce_variants.cuh"
 using namespace zkb;
 
+// D: sums kept in [0, 2^128) instead of [0, p): a + v only wraps on a carry out of 2^128 (v canonical, so a + v - p fits);
+//    differences and products accept such operands unchanged.  Outputs are canonicalised once at the end.
+__device__ __forceinline__ fe add_lazy(const fe& a, const fe& b) {
+    fe s; uint32_t cy;
+    asm("add.cc.u32 %0, %5, %9;\n\t addc.cc.u32 %1, %6, %10;\n\t addc.cc.u32 %2, %7, %11;\n\t addc.cc.u32 %3, %8, %12;\n\t addc.u32 %4, 0, 0;"
+        : "=r"(s.x[0]), "=r"(s.x[1]), "=r"(s.x[2]), "=r"(s.x[3]), "=r"(cy)
+        : "r"(a.x[0]), "r"(a.x[1]), "r"(a.x[2]), "r"(a.x[3]), "r"(b.x[0]), "r"(b.x[1]), "r"(b.x[2]), "r"(b.x[3]));
+    const uint32_t m = 0u - cy;
+    asm("add.cc.u32 %0, %0, %4;\n\t addc.cc.u32 %1, %1, %5;\n\t addc.cc.u32 %2, %2, 0;\n\t addc.u32 %3, %3, 0;"
+        : "+r"(s.x[0]), "+r"(s.x[1]), "+r"(s.x[2]), "+r"(s.x[3]) : "r"(m & ZKB_C0), "r"(m & ZKB_C1));
+    return s;
+}
 #ifndef UNITS
 #define UNITS 8
 #endif
@@ -23,14 +35,14 @@ __global__ void __launch_bounds__(256) k(fe* io, const fe* tw, int iters) {
     for (int i = 0; i < iters; i++) {
 #pragma unroll
         for (int u = 0; u < UNITS; u++) {
-            const fe v = mulv<V>(y[u], w);
+            const fe v = mulv<(V == 3 ? 0 : V)>(y[u], w);
             const fe a = x[u];
-            x[u] = fe_add(a, v);
+            x[u] = V == 3 ? add_lazy(a, v) : fe_add(a, v);
             y[u] = fe_sub(a, v);
         }
     }
 #pragma unroll
-    for (int u = 0; u < UNITS; u++) { fe_store(io + (size_t)t * 2 * UNITS + 2 * u, x[u]); fe_store(io + (size_t)t * 2 * UNITS + 2 * u + 1, y[u]); }
+    for (int u = 0; u < UNITS; u++) { if (V == 3) { x[u] = fe_canon(x[u], 0); y[u] = fe_canon(y[u], 0); } fe_store(io + (size_t)t * 2 * UNITS + 2 * u, x[u]); fe_store(io + (size_t)t * 2 * UNITS + 2 * u + 1, y[u]); }
 }
 
 template <int V> void run(const char* name, fe* io, fe* tw, unsigned long long* ref, bool check) {
@@ -63,5 +75,6 @@ int main() {
     run<0>("A mad-chain folds (shipped)", io, tw, ref, false);
     run<1>("B (hi*45)<<40 - hi", io, tw, ref, true);
     run<2>("C (hi<<32) - hi + hi*c1<<32", io, tw, ref, true);
+    run<3>("D shipped mul, non-canonical sums", io, tw, ref, true);
     return 0;
 }
