@@ -32,10 +32,12 @@ __global__ void __launch_bounds__(256) k(fe* io, const fe* tw, int iters) {
 #pragma unroll
     for (int u = 0; u < UNITS; u++) { x[u] = fe_load(io + (size_t)t * 2 * UNITS + 2 * u); y[u] = fe_load(io + (size_t)t * 2 * UNITS + 2 * u + 1); }
     const fe w = fe_load(tw + (threadIdx.x & 31));
+    fe4 w4;
+    if (V == 5) { fe sh = fe_zero(); sh.x[1] = 1; w4.w[0] = fe_canon(w, 0); for (int i = 1; i < 4; i++) w4.w[i] = fe_mul(w4.w[i - 1], sh); }
     for (int i = 0; i < iters; i++) {
 #pragma unroll
         for (int u = 0; u < UNITS; u++) {
-            const fe v = mulv<(V == 3 ? 0 : V)>(y[u], w);
+            const fe v = V == 5 ? mul_pre4(y[u], w4) : mulv<(V == 3 ? 0 : V)>(y[u], w);
             const fe a = x[u];
             x[u] = V == 3 ? add_lazy(a, v) : fe_add(a, v);
             y[u] = fe_sub(a, v);
@@ -76,5 +78,7 @@ int main() {
     run<1>("B (hi*45)<<40 - hi", io, tw, ref, true);
     run<2>("C (hi<<32) - hi + hi*c1<<32", io, tw, ref, true);
     run<3>("D shipped mul, non-canonical sums", io, tw, ref, true);
+    run<4>("E k = 0x2D00 fold (no *0xFFFFFFFF)", io, tw, ref, true);
+    run<5>("F 4 pre-shifted twiddle copies", io, tw, ref, true);
     return 0;
 }

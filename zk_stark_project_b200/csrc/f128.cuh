@@ -3,9 +3,8 @@
 // src/aggregation/prover.rs:12): p = 2^128 - 45*2^40 + 1, canonical little-endian u128.
 //
 // Elements are four 32-bit limbs in registers (one uint4 / 128-bit access in memory).  A product is
-// 16 IMAD.WIDE on the FMA pipe (even/odd carry chains) folded twice with 2^128 = C (mod p),
-// C = 45*2^40 - 1 = {0xFFFFFFFF, 0x2CFF}; the fold is itself done with multiply-accumulate chains so
-// the work is split between the FMA and ALU pipes instead of piling onto the ALU pipe.
+// 16 IMAD.WIDE (even/odd carry chains) folded twice with 2^128 = C (mod p), C = 45*2^40 - 1 = K*2^32 - 1,
+// K = 0x2D00: the folds multiply by the 14-bit K only (fe_reduce256).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -137,46 +136,39 @@ __device__ __forceinline__ void mul_wide(const fe& a, const fe& b, uint32_t r[8]
           "r"(o0), "r"(o1), "r"(o2), "r"(o3), "r"(o4), "r"(o5), "r"(o6));
 }
 
-// lo(128) + hi(128) * 2^128  ->  canonical element
+// lo(128) + hi(128) * 2^128  ->  canonical element (any 256-bit input).
+// 2^128 = K*2^32 - 1 (mod p) with K = 45*2^8 = 0x2D00, so hi*2^128 = ((hi*K) << 32) - hi: every product is an IMAD.WIDE by a
+// 14-bit immediate and the 32-bit shift is a limb move.  (Folding with C = {0xFFFFFFFF, 0x2CFF} instead makes ptxas split the
+// products by 0xFFFFFFFF into IMAD + quarter-rate IMAD.HI: 98.6 -> 87.3 SASS instructions per butterfly, 203.6 -> 237.2 G
+// butterflies/s register-resident on B200, tools/mul_variants.cu variant E, profiles/r2_mul_variants.txt.)
+//   U  = lo - hi + ((hi*K) << 32)                 six limbs, two's complement while negative, 0 <= U < 2^175
+//   r  = U mod 2^128 + ((top*K) << 32) - top      top = U >> 128 < 2^47;  r < 2^128 + 2^93, so at most one wrap
 __device__ __forceinline__ fe fe_reduce256(const uint32_t v[8]) {
-    uint32_t r0 = v[0], r1 = v[1], r2 = v[2], r3 = v[3], r4, r5;
-    uint32_t o0, o1, o2, o3, o4;
-    const uint32_t h0 = v[4], h1 = v[5], h2 = v[6], h3 = v[7];
-    const uint32_t c0 = ZKB_C0, c1 = ZKB_C1;
-    // first fold: (r0..r5) = lo + hi * C
+    const uint32_t k = 0x2D00u;
+    uint32_t d0, d1, d2, d3, d4, d5, o0, o1, o2, o3;
     asm("{\n\t"
-        "mad.lo.cc.u32 %0, %11, %15, %0;\n\t madc.hi.cc.u32 %1, %11, %15, %1;\n\t"
-        "madc.lo.cc.u32 %2, %13, %15, %2;\n\t madc.hi.cc.u32 %3, %13, %15, %3;\n\t"
-        "addc.u32 %4, 0, 0;\n\t"
-        "mad.lo.cc.u32 %2, %12, %16, %2;\n\t madc.hi.cc.u32 %3, %12, %16, %3;\n\t"
-        "madc.lo.cc.u32 %4, %14, %16, %4;\n\t madc.hi.u32 %5, %14, %16, 0;\n\t"
-        "mul.lo.u32 %6, %12, %15;\n\t mul.hi.u32 %7, %12, %15;\n\t"
-        "mul.lo.u32 %8, %14, %15;\n\t mul.hi.u32 %9, %14, %15;\n\t"
-        "mad.lo.cc.u32 %6, %11, %16, %6;\n\t madc.hi.cc.u32 %7, %11, %16, %7;\n\t"
-        "madc.lo.cc.u32 %8, %13, %16, %8;\n\t madc.hi.cc.u32 %9, %13, %16, %9;\n\t"
-        "addc.u32 %10, 0, 0;\n\t"
-        "add.cc.u32 %1, %1, %6;\n\t addc.cc.u32 %2, %2, %7;\n\t addc.cc.u32 %3, %3, %8;\n\t"
-        "addc.cc.u32 %4, %4, %9;\n\t addc.u32 %5, %5, %10;\n\t"
+        "sub.cc.u32 %0, %10, %14;\n\t subc.cc.u32 %1, %11, %15;\n\t subc.cc.u32 %2, %12, %16;\n\t subc.cc.u32 %3, %13, %17;\n\t"
+        "subc.u32 %4, 0, 0;\n\t mov.u32 %5, %4;\n\t"                                   // sign extension of lo - hi
+        "mad.lo.cc.u32 %1, %14, %18, %1;\n\t madc.hi.cc.u32 %2, %14, %18, %2;\n\t"     // (d1,d2) += h0 K
+        "madc.lo.cc.u32 %3, %16, %18, %3;\n\t madc.hi.cc.u32 %4, %16, %18, %4;\n\t"    // (d3,d4) += h2 K
+        "addc.u32 %5, %5, 0;\n\t"
+        "mul.lo.u32 %6, %15, %18;\n\t mul.hi.u32 %7, %15, %18;\n\t"                    // (o0,o1) = h1 K
+        "mul.lo.u32 %8, %17, %18;\n\t mul.hi.u32 %9, %17, %18;\n\t"                    // (o2,o3) = h3 K
+        "add.cc.u32 %2, %2, %6;\n\t addc.cc.u32 %3, %3, %7;\n\t addc.cc.u32 %4, %4, %8;\n\t addc.u32 %5, %5, %9;\n\t"
         "}"
-        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "=&r"(r4), "=&r"(r5),
-          "=&r"(o0), "=&r"(o1), "=&r"(o2), "=&r"(o3), "=&r"(o4)
-        : "r"(h0), "r"(h1), "r"(h2), "r"(h3), "r"(c0), "r"(c1));
-    // second fold: top = r5:r4 < 2^46;  r += top * C, counting wraps of 2^128 (at most one)
-    uint32_t cy;
+        : "=&r"(d0), "=&r"(d1), "=&r"(d2), "=&r"(d3), "=&r"(d4), "=&r"(d5), "=&r"(o0), "=&r"(o1), "=&r"(o2), "=&r"(o3)
+        : "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(k));
+    // second fold: W = ((top*K) << 32) - top, three limbs, >= 0
+    uint32_t q0, q1, w0, w1, w2, cy;
+    fe out;
     asm("{\n\t"
-        ".reg .u32 t;\n\t"
-        "mul.lo.u32 t, %6, %8;\n\t"  // t1*c1 < 2^28, weight 2^64
-        "mad.lo.cc.u32 %0, %5, %7, %0;\n\t madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
-        "addc.cc.u32 %2, %2, t;\n\t addc.cc.u32 %3, %3, 0;\n\t addc.u32 %4, 0, 0;\n\t"
-        "mad.lo.cc.u32 %1, %5, %8, %1;\n\t madc.hi.cc.u32 %2, %5, %8, %2;\n\t"
-        "addc.cc.u32 %3, %3, 0;\n\t addc.u32 %4, %4, 0;\n\t"
-        "mad.lo.cc.u32 %1, %6, %7, %1;\n\t madc.hi.cc.u32 %2, %6, %7, %2;\n\t"
-        "addc.cc.u32 %3, %3, 0;\n\t addc.u32 %4, %4, 0;\n\t"
+        "mul.lo.u32 %0, %10, %12;\n\t mul.hi.u32 %1, %10, %12;\n\t mad.lo.u32 %1, %11, %12, %1;\n\t"
+        "sub.cc.u32 %2, 0, %10;\n\t subc.cc.u32 %3, %0, %11;\n\t subc.u32 %4, %1, 0;\n\t"
+        "add.cc.u32 %5, %13, %2;\n\t addc.cc.u32 %6, %14, %3;\n\t addc.cc.u32 %7, %15, %4;\n\t addc.cc.u32 %8, %16, 0;\n\t addc.u32 %9, 0, 0;\n\t"
         "}"
-        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "=&r"(cy)
-        : "r"(r4), "r"(r5), "r"(c0), "r"(c1));
+        : "=&r"(q0), "=&r"(q1), "=&r"(w0), "=&r"(w1), "=&r"(w2), "=&r"(out.x[0]), "=&r"(out.x[1]), "=&r"(out.x[2]), "=&r"(out.x[3]), "=&r"(cy)
+        : "r"(d4), "r"(d5), "r"(k), "r"(d0), "r"(d1), "r"(d2), "r"(d3));
     // a wrap (cy) and "value >= p" are both fixed by adding C modulo 2^128
-    fe out; out.x[0] = r0; out.x[1] = r1; out.x[2] = r2; out.x[3] = r3;
     return fe_canon(out, cy);
 }
 
