@@ -182,10 +182,11 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "stark_proofs_per_sec", "value": val, "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u128 mod p (f128 field), u32 BLAKE3", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "options": "40 queries, grinding 21, FRI folding 16, remainder degree <= 7"},
+        "config": {"workload": f"{args.workload}: {desc}", "options": OPTIONS_TEXT, "l2": l2_text(n, w, beta)},
         "cpu_baseline": {"value": val, "unit": "proofs/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} full proofs of the workload (C++ restatement of Winterfell 0.12's CPU prover; "
-                                   "the Rust reference itself cannot be built in this image: no cargo/rustc)"},
+                         "sample": f"{args.steps} full proofs of the workload (C++ restatement of Winterfell 0.12's CPU prover, std::thread on all host cores, "
+                                   "portable scalar BLAKE3 - upstream uses the SIMD blake3 crate; the Rust reference itself cannot be built in this image: "
+                                   "no cargo/rustc)"},
         "e2e": {"value": val, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -272,6 +273,74 @@ def run_mimc_helpers(args):
           "gpu_launches": ctx.launches(), "cases": cases, "cpu_baseline": cpu})
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum over the K1+K2 launches of ONE proof (transpose, interpolation passes, LDE passes),
+# from an `ncu --set full` capture of that workload; None = not captured (never extrapolated).  Two passes through HBM per
+# 2^16-point transform (a shared-memory tile holds 2^8 rows x 16 columns) make this 2.8x the algorithmic bytes.
+NCU_TRAFFIC = {
+    "training_2p16": (13.580e9, "profiles/r1_ncu_k1k2_dram_traffic.csv (kernel structure unchanged in round 2: same tiles, same passes)"),
+}
+OPTIONS_TEXT = "40 queries, grinding 21, FRI folding 16, remainder degree <= 7"
+
+
+def l2_text(n, w, beta):
+    return "inputs larger than L2 (trace %d MiB, LDE %d MiB)" % ((w * n * 16) >> 20, (w * n * 16 * beta) >> 20)
+
+
+def counter_felts(w, n, seed, col0=0, cols=None):
+    """Counter-based synthetic trace (so that a rank can build just its own columns): cell (j, i) = splitmix64 of a per-cell
+    counter, hi word < 2^63 (canonical).  Returns a (cols, n, 2) uint64 array for columns [col0, col0 + cols)."""
+    cols = w if cols is None else cols
+    out = np.empty((cols, n, 2), dtype=np.uint64)
+
+    def mix(x):
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+    idx = np.arange(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        for j in range(cols):
+            base = np.uint64((seed * 0x100000001B3 + (col0 + j) * 2 * n) & 0xFFFFFFFFFFFFFFFF)
+            out[j, :, 0] = mix(base + idx)
+            out[j, :, 1] = mix(base + np.uint64(n) + idx) >> np.uint64(1)
+    return out
+
+
+def training_air_from_rows(n, w, opts, first, last):
+    """Training AIR description from the boundary rows only (what get_pub_inputs reads, src/training/prover.rs:245-246)."""
+    data = np.zeros((w, 2, 2), dtype=np.uint64)
+    for j in range(w):
+        data[j, 0, 0], data[j, 0, 1] = first[j] & 0xFFFFFFFFFFFFFFFF, first[j] >> 64
+        data[j, 1, 0], data[j, 1, 1] = last[j] & 0xFFFFFFFFFFFFFFFF, last[j] >> 64
+    from zk_stark_project_b200 import synthetic as S
+
+    class _View:  # rows 0 and n-1 of the trace, addressed like the full array
+        shape = (w, n, 2)
+
+        def __getitem__(self, key):
+            c, r, q = key
+            return data[c, 0 if r == 0 else 1, q]
+    return S.synthetic_training_air(n, opts, _View())
+
+
+def roofline_of(workload, n, w_local, beta, lde_ms, alg_lde, peak, peak_src, sharded=False):
+    achieved = alg_lde / (lde_ms * 1e-3) / 1e9
+    traffic = NCU_TRAFFIC.get(workload) if not sharded else None
+    bf = w_local * (n // 2) * (n.bit_length() - 1) * (beta + 1)
+    return {
+        "roofline": {"bound": "hbm", "kernel": "k_ntt_pass (K1 interpolation + K2 coset LDE)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic[0] if traffic else None,
+                     "traffic_source": traffic[1] if traffic else "no ncu --set full capture of this workload",
+                     "peak_source": peak_src, "algorithmic_bytes_per_proof": alg_lde, "kernel_ms_per_proof": lde_ms,
+                     "note": "bound by integer issue, not HBM: a radix-2 f128 butterfly is ~87 SASS integer instructions per 32 bytes moved "
+                             "(profiles/r2_mul_variants.txt, profiles/r2_sass_hist_k_ntt_pass.txt); ncu: issue-slot utilisation ~55%, DRAM 10-20%"},
+        # what actually bounds K1/K2: integer issue.  Peak = register-resident radix-2 f128 butterflies/s of the shipped multiplier on this
+        # pool's B200 (tools/mul_variants.cu variant E; no memory traffic at all)
+        "compute_roofline": {"unit": "G butterflies/s", "peak": 237.2, "achieved": bf / (lde_ms * 1e-3) / 1e9,
+                             "frac": bf / (lde_ms * 1e-3) / 1e9 / 237.2, "source": "tools/mul_variants.cu variant E, profiles/r2_mul_variants.txt"},
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -280,12 +349,14 @@ def main():
     ap.add_argument("--workload", default="training_2p16", choices=sorted(WORKLOADS) + ["mimc_helpers"])
     ap.add_argument("--impl", default="zkb200", choices=["zkb200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle timing at N=1")
+    ap.add_argument("--no-headline", action="store_true", help="N=1: skip the 2^20-row-trace proofs (MiMC 64 x 2^20, training shape 240 x 2^20)")
+    ap.add_argument("--no-sharded", action="store_true", help="N>1: skip the column-sharded single proof after the replica arm")
     ap.add_argument("--inflight", type=int, default=0,
                     help="independent proofs in flight per GPU in the throughput arms (one zkb_ctx + CUDA stream + host thread each; 0 = 4, or 2 on hosts with few cores); "
                          "single-proof latency is always measured too and reported as prove_ms")
     ap.add_argument("--sharded", action="store_true",
-                    help="ONE proof per step, column-sharded across all ranks (NVLink all-to-all; strong scaling) instead of one "
-                         "independent proof per rank; MiMC workloads only (64 columns)")
+                    help="make the column-sharded proof of --workload the MAIN arm (ONE proof per step across all ranks, strong scaling) "
+                         "instead of one independent proof stream per rank")
     args = ap.parse_args()
     capture_stdout()
 
@@ -316,11 +387,35 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_ranks(*vals):
+        if world == 1:
+            return [float(v) for v in vals]
+        t = torch.tensor(list(vals), device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+
     kind, n, w, beta, desc = WORKLOADS[args.workload]
     sharded = args.sharded and world > 1
     if args.sharded and kind == "aggregation":
         raise SystemExit("--sharded: the aggregation AIR couples columns i and i+60 and cannot be column-sharded")
     ctx = L.Context(local_rank)  # default stream: the same stream torch.cuda.Event records on
+    mg_ready = False
+
+    def ensure_mg():
+        nonlocal mg_ready
+        if not mg_ready:
+            from zk_stark_project_b200 import multi_gpu as M
+            M.init_sharded(ctx, rank, world, dist)
+            mg_ready = True
+
     seed_rank = 0 if sharded else rank  # a sharded proof is ONE trace shared by all ranks
     air, data, opts = build_workload(args.workload, 0x5EED0000 + seed_rank)
     if kind == "mimc":
@@ -331,8 +426,7 @@ def main():
         air = mimc_air(opts, w, n, [get(j, 0) for j in range(w)], [get(j, n - 1) for j in range(w)])
     w_local = w // world if sharded else w
     if sharded:
-        from zk_stark_project_b200 import multi_gpu as M
-        M.init_sharded(ctx, rank, world, dist)
+        ensure_mg()
         data = data[rank * w_local:(rank + 1) * w_local]  # (every rank built the same seeded trace; it keeps its columns)
     nbytes = w_local * n * 16
     pinned = L.PinnedBuffer(nbytes)
@@ -340,7 +434,6 @@ def main():
     d_trace = ctx.upload_trace(pinned.ptr, w_local, n)
     air_dict, air = air, ctx.prepare(air)  # marshal the AIR description once, outside the timed regions
     prove_device = (lambda: ctx.mg_prove_device(air, d_trace)) if sharded else (lambda: ctx.prove_device(air, d_trace))
-    prove_host = (lambda: ctx.mg_prove_host(air, pinned.ptr, world)) if sharded else (lambda: ctx.prove_host(air, pinned.ptr))
 
     ce = 8 if kind == "mimc" else 2
     c = 6 if kind == "mimc" else 1
@@ -426,33 +519,162 @@ def main():
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     sampler.stop()
-    proof_e2e = res[0][0]
     assert all(r[0] == proof for r in res), "e2e proof differs from the device-resident proof"
 
+    ms, ms_e2e, ms_latency = max_ranks(ms, ms_e2e, ms_latency)
     if world > 1:
-        t = torch.tensor([ms, ms_e2e, ms_latency], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, ms_latency = float(t[0]), float(t[1]), float(t[2])
         lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt[0])
+    stages = {k_: v_ / args.steps for k_, v_ in stage_acc.items()}
+    main_proof_len = len(proof)
+    tb_main = bytes(pinned.view()) if (world == 1 and not args.no_cpu_baseline) else None
+
+    # release the lanes: the next sections need the memory
+    for c2, _, p2 in lanes[1:]:
+        c2.close()
+        p2.free()
+    lanes = lanes[:1]
+    pinned.free()
+
+    def single_proof_case(name, steps, warm):
+        """One proof at a time of workload `name` on this rank's context: device-resident latency, end-to-end latency from pinned
+        host columns, stage times, roofline of the LDE stage.  Used for the 2^20-row-trace headline (N = 1)."""
+        k2, n2, w2, b2, d2 = WORKLOADS[name]
+        o2 = Z.ProofOptions(40, b2, 21, Z.FieldExtension.NONE, 16, 7)
+        nb = w2 * n2 * 16
+        pin = L.PinnedBuffer(nb)
+        if k2 == "mimc":
+            dptr = ctx.mimc_trace([j + 1 for j in range(w2)], n2, Z.get_round_constants(), device=True)
+            pin.view()[:] = np.frombuffer(ctx.download(dptr, nb), dtype=np.uint8)
+            arr = pin.view().view(np.uint64).reshape(w2, n2, 2)
+            gv = lambda cc, r: int(arr[cc, r, 0]) | (int(arr[cc, r, 1]) << 64)
+            a2 = mimc_air(o2, w2, n2, [gv(j, 0) for j in range(w2)], [gv(j, n2 - 1) for j in range(w2)])
+        else:
+            arr = pin.view().view(np.uint64).reshape(w2, n2, 2)
+            arr[:] = counter_felts(w2, n2, 0x5EED2000)
+            gv = lambda cc, r: int(arr[cc, r, 0]) | (int(arr[cc, r, 1]) << 64)
+            a2 = training_air_from_rows(n2, w2, o2, [gv(j, 0) for j in range(w2)], [gv(j, n2 - 1) for j in range(w2)])
+            dptr = ctx.upload_trace(pin.ptr, w2, n2)
+        a2 = ctx.prepare(a2)
+        for _ in range(warm):
+            pr, _ = ctx.prove_device(a2, dptr)
+        acc = {}
+        torch.cuda.synchronize()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for _ in range(steps):
+            pr2, _ = ctx.prove_device(a2, dptr)
+            for k_, v_ in ctx.stage_times().items():
+                acc[k_] = acc.get(k_, 0.0) + v_ / steps
+        h1.record()
+        torch.cuda.synchronize()
+        assert pr2 == pr
+        dev_ms = h0.elapsed_time(h1) / steps
+        ctx.prove_host(a2, pin.ptr)
+        h0.record()
+        for _ in range(steps):
+            pr3, _ = ctx.prove_host(a2, pin.ptr)
+        h1.record()
+        torch.cuda.synchronize()
+        assert pr3 == pr, "e2e proof differs from the device-resident proof"
+        e2e_ms = h0.elapsed_time(h1) / steps
+        pin.free()
+        ce2, c2_ = (8, 6) if k2 == "mimc" else (2, 1)
+        al = algorithmic_bytes(n2, w2, b2, ce2, c2_)
+        rec = {"workload": f"{name}: {d2}", "prove_ms": dev_ms, "e2e_ms": e2e_ms, "h2d_bytes": nb, "d2h_bytes": len(pr), "proof_bytes": len(pr),
+               "steps": steps, "algorithmic_bytes": al["total"], "t_hbm_ms": al["total"] / peak / 1e6, "proof_roofline_frac": (al["total"] / peak / 1e6) / dev_ms,
+               "stages_ms": {k_: round(v_, 3) for k_, v_ in acc.items() if v_ > 0 and k_ not in ("total", "h2d")}}
+        rec.update(roofline_of(name, n2, w2, b2, max(acc.get("lde", 0.0), 1e-6), al["lde"] + al["interp"], peak, peak_src))
+        return rec
+
+    def sharded_case(name, steps, warm):
+        """ONE proof of workload `name`, column-sharded over all ranks (zkb_mg_prove_device: NVLink all-to-all + all-gathers), timed
+        as the max over ranks and compared byte for byte on rank 0 with the single-GPU proof (zkb_prove_device) of the same trace."""
+        ensure_mg()
+        k2, n2, w2, b2, d2 = WORKLOADS[name]
+        o2 = Z.ProofOptions(40, b2, 21, Z.FieldExtension.NONE, 16, 7)
+        wl = w2 // world
+        if k2 == "mimc":
+            # every rank runs the (deterministic) chain generator for all columns; its own columns are a contiguous slice
+            dfull = ctx.mimc_trace([j + 1 for j in range(w2)], n2, Z.get_round_constants(), device=True)
+            edge = lambda r: [int.from_bytes(ctx.download(dfull + (j * n2 + r) * 16, 16), "little") for j in range(w2)]
+            a2 = mimc_air(o2, w2, n2, edge(0), edge(n2 - 1))
+            dloc = dfull + rank * wl * n2 * 16
+            pin = None
+        else:
+            # counter-based trace: a rank builds only its columns; rank 0 also builds the whole trace for the single-GPU proof
+            mine = counter_felts(w2, n2, 0x5EED2000, rank * wl, wl)
+            rows = torch.tensor(np.stack([mine[:, 0, :], mine[:, n2 - 1, :]]).astype(np.int64), device="cuda")
+            allrows = [torch.empty_like(rows) for _ in range(world)]
+            dist.all_gather(allrows, rows)
+            fl = np.concatenate([t.cpu().numpy().astype(np.uint64) for t in allrows], axis=1)   # (2, w, 2)
+            val = lambda r, j: int(fl[r, j, 0]) | (int(fl[r, j, 1]) << 64)
+            a2 = training_air_from_rows(n2, w2, o2, [val(0, j) for j in range(w2)], [val(1, j) for j in range(w2)])
+            pin = L.PinnedBuffer(wl * n2 * 16)
+            pin.view()[:] = mine.reshape(-1).view(np.uint8)
+            dloc = ctx.upload_trace(pin.ptr, wl, n2)
+            dfull = None
+        a2 = ctx.prepare(a2)
+        for _ in range(warm):
+            pr, _ = ctx.mg_prove_device(a2, dloc)
+        acc = {}
+        barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for _ in range(steps):
+            pr, _ = ctx.mg_prove_device(a2, dloc)
+            for k_, v_ in ctx.stage_times().items():
+                acc[k_] = acc.get(k_, 0.0) + v_ / steps
+        h1.record()
+        barrier()
+        sh_ms = h0.elapsed_time(h1) / steps
+        (sh_ms,) = max_ranks(sh_ms)
+        import hashlib
+        digs = [None] * world
+        dist.all_gather_object(digs, hashlib.sha256(pr).hexdigest())
+        same_on_all = len(set(digs)) == 1
+        rec = None
+        single_ms, parity = None, None
+        if rank == 0:
+            if k2 != "mimc":
+                if pin is not None:
+                    pin.free()
+                full = L.PinnedBuffer(w2 * n2 * 16)
+                full.view().view(np.uint64).reshape(w2, n2, 2)[:] = counter_felts(w2, n2, 0x5EED2000)
+                dfull = ctx.upload_trace(full.ptr, w2, n2)
+                full.free()
+            ref, _ = ctx.prove_device(a2, dfull)
+            torch.cuda.synchronize()
+            h0.record()
+            for _ in range(max(1, steps - 1)):
+                ref, _ = ctx.prove_device(a2, dfull)
+            h1.record()
+            torch.cuda.synchronize()
+            single_ms = h0.elapsed_time(h1) / max(1, steps - 1)
+            parity = bool(ref == pr and same_on_all)
+            rec = {"workload": f"{name}: {d2}", "n_gpus": world, "prove_ms": sh_ms, "single_gpu_ms": single_ms, "speedup": single_ms / sh_ms,
+                   "parity": parity, "parity_checked_against": "zkb_prove_device proof of the same trace on rank 0 (byte comparison); all ranks returned the same bytes: %s" % same_on_all,
+                   "xchg_exposed_ms": round(acc.get("interpolate", 0.0), 4), "proof_bytes": len(pr), "steps": steps,
+                   "stages_ms": {k_: round(v_, 3) for k_, v_ in acc.items() if v_ > 0 and k_ not in ("total", "h2d", "interpolate")}}
+        barrier()
+        return rec
+
+    headline, sharded_recs = None, None
+    if world == 1 and not args.no_headline and not sharded:
+        headline = {"mimc": single_proof_case("mimc_2p20", 3, 1), "training": single_proof_case("training_2p20", 3, 1)}
+    if world > 1 and not args.no_sharded and not sharded:
+        sharded_recs = [sharded_case("mimc_2p20", 3, 1)]
+        if world >= 4:
+            sharded_recs.append(sharded_case("training_2p20", 2, 1))
 
     proofs_per_step = 1 if sharded else world * inflight
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-        stages = {k_: v_ / args.steps for k_, v_ in stage_acc.items()}
         # interpolation (K1) and the coset LDE (K2) are interleaved per column group inside the library and timed together
         alg["lde"] += alg["interp"]
         if sharded:  # this rank transforms w/G columns
             alg["lde"] //= world
         lde_ms = max(stages.get("lde", 0.0), 1e-6)
-        achieved = alg["lde"] / (lde_ms * 1e-3) / 1e9
         # per-stage achieved bandwidth against the same peak, for the profile notes
         per_stage = {}
         for st, key in (("lde", "lde"), ("leaf_hash", "leaf"), ("merkle", "merkle"), ("constraints", "ceval"),
@@ -469,47 +691,41 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if sharded else "weak",
             "vs_baseline": None, "dtype": "u128 mod p (f128 field, 4x u32 limbs), u32 BLAKE3", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "options": "40 queries, grinding 21, FRI folding 16, remainder degree <= 7",
-                       "proofs_per_gpu_per_step": inflight, "l2": "inputs larger than L2 (trace %d MiB, LDE %d MiB)" % (nbytes >> 20, (nbytes * beta) >> 20),
-                       "proof_bytes": len(proof),
-                       "parallelism": (f"one proof column-sharded over {world} GPUs: NCCL all-to-all (NVLink transpose) + all-gathers" if sharded
-                                       else f"{world} independent proof stream(s), one per GPU, no data-path collective")},
+            "config": {"workload": f"{args.workload}: {desc}", "options": OPTIONS_TEXT, "l2": l2_text(n, w, beta)},
+            "run": {"proofs_per_gpu_per_step": inflight, "proof_bytes": main_proof_len,
+                    "parallelism": (f"one proof column-sharded over {world} GPUs: NCCL all-to-all (NVLink transpose) + all-gathers" if sharded
+                                    else f"{world} independent proof stream(s), one per GPU, no data-path collective")},
             "prove_ms": ms_latency / args.steps,
-            "roofline": {"bound": "hbm", "kernel": "k_ntt_pass (K1 interpolation + K2 coset LDE)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak,
-                         # dram__bytes_read+write summed over the K1+K2 launches of one proof (transpose, 2 interpolation passes, 2 LDE
-                         # passes; ncu, profiles/r1_ncu_k1k2_dram_traffic.csv): 2.8x the algorithmic bytes because n = 2^16 needs two
-                         # passes through HBM per transform (a shared-memory tile holds 2^8 rows x 16 columns)
-                         "traffic": 13.580e9 if args.workload == "training_2p16" and not sharded else None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_proof": alg["lde"], "kernel_ms_per_proof": lde_ms,
-                         "note": "bound by integer issue (FMA-heavy + ALU pipes), not HBM: a radix-2 f128 butterfly is ~100 SASS integer instructions "
-                                 "per 32 bytes moved; ncu: sm__pipe_fmaheavy_cycles_active 75%, ALU 57%, DRAM 9-17% (profiles/r1_ncu_ntt_lde_final.txt)"},
-            # what actually bounds K1/K2: integer issue.  Peak = register-resident radix-2 f128 butterflies/s measured on this pool's
-            # B200 by tools/mul_variants.cu (no memory traffic at all; profiles/r1_mul_variants_butterfly_peak.txt)
-            "compute_roofline": {"unit": "G butterflies/s", "peak": 203.5,
-                                 "achieved": (w_local * (n // 2) * (n.bit_length() - 1) * (beta + 1)) / (lde_ms * 1e-3) / 1e9,
-                                 "frac": (w_local * (n // 2) * (n.bit_length() - 1) * (beta + 1)) / (lde_ms * 1e-3) / 1e9 / 203.5,
-                                 "leaf_hash_alu_pipe_pct": 95.8, "source": "tools/mul_variants.cu, profiles/r1_ncu_hash_lde_rows.txt"},
             "proof_roofline": {"algorithmic_bytes": alg["total"], "t_hbm_ms": alg["total"] / peak / 1e6,
                                "frac": (alg["total"] / peak / 1e6) / (ms_latency / args.steps)},
             "stages": per_stage,
             "e2e": {"value": proofs_per_step * args.steps / (ms_e2e * 1e-3), "unit": "proofs/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": nbytes * (world if sharded else world * inflight),
-                    "d2h_bytes_per_step": len(proof) * (1 if sharded else world * inflight)},
+                    "d2h_bytes_per_step": main_proof_len * (1 if sharded else world * inflight)},
             "gpu_launches": launches,
             "clocks": sampler.summary(t_wall0, t_wall1),
         }
+        line.update(roofline_of(args.workload, n, w_local, beta, lde_ms, alg["lde"], peak, peak_src, sharded))
+        line["compute_roofline"]["leaf_hash_alu_pipe_pct"] = 95.8
+        if headline:
+            # BASELINE.json `metric`, first half: prove time of a 2^20-ROW TRACE on one B200, measured in this same run
+            line["headline_2p20"] = headline
+        if sharded_recs:
+            # BASELINE.json configs[4]: one large proof column-sharded over the ranks, checked against the single-GPU proof
+            line["sharded"] = sharded_recs[0]
+            if len(sharded_recs) > 1:
+                line["sharded_training_2p20"] = sharded_recs[1]
         if world == 1 and not args.no_cpu_baseline:
             from oracle import pyoracle as O
             O.build()
             cores = os.cpu_count() or 1
             O.set_threads(cores)
-            tb = bytes(pinned.view())  # world == 1 here, so the pinned buffer holds the whole trace
             t0 = time.time()
-            ref, ts_ref, secs = O.prove(air_dict, tb)
+            ref, ts_ref, secs = O.prove(air_dict, tb_main)
             dt = time.time() - t0
             line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "proofs/s", "ms_per_proof": dt * 1e3, "cores": cores, "kind": "port",
-                                    "sample": "1 full proof of the same workload (C++ restatement of Winterfell's CPU prover, all host cores)",
+                                    "sample": "1 full proof of the same workload (C++ restatement of Winterfell's CPU prover: std::thread over columns / rows on "
+                                              "all host cores, portable scalar BLAKE3 - upstream uses the SIMD blake3 crate; not Winterfell itself)",
                                     "proof_identical_to_gpu": ref == proof}
         emit(line)
     if world > 1:

@@ -127,8 +127,14 @@ int32_t zkb_begin(zkb_ctx* ctx, const zkb_air_desc* air);
 /* Prover::new_trace_lde -> DefaultTraceLde::new (src/training/prover.rs:273-281): K1-K4 */
 int32_t zkb_trace_commit(zkb_ctx* ctx, const uint8_t* const* cols, uint8_t root_out[32]);
 int32_t zkb_trace_commit_device(zkb_ctx* ctx, const void* d_trace_colmajor, uint8_t root_out[32]);
-/* TraceLde::read_main_trace_frame_into: current and next row of LDE step `lde_step` */
+/* TraceLde::read_main_trace_frame_into: current and next row of LDE step `lde_step`
+ * (next = row lde_step + blowup, wrapping around the LDE domain).  One host round trip per call. */
 int32_t zkb_trace_read_frame(zkb_ctx* ctx, uint64_t lde_step, uint8_t* current_out, uint8_t* next_out);
+/* the same for `count` steps in ONE round trip: current_out / next_out hold count rows of trace_width elements each.
+ * Winterfell's DefaultConstraintEvaluator reads one frame per constraint-evaluation point from rayon threads (TraceLde: Sync);
+ * a context is single-threaded and a round trip costs ~20 us, so a caller that keeps the default evaluator must batch its
+ * reads through this call — the intended pairing is zkb_constraints_eval, which never moves frames to the host. */
+int32_t zkb_trace_read_frames(zkb_ctx* ctx, const uint64_t* lde_steps, uint32_t count, uint8_t* current_out, uint8_t* next_out);
 /* TracePolyTable contents, row-major [n][w] coefficients (only needed if the host keeps DEEP) */
 int32_t zkb_trace_polys_read(zkb_ctx* ctx, uint8_t* out);
 /* Prover::new_evaluator + ConstraintEvaluator::evaluate (src/training/prover.rs:283-290): K5.
@@ -187,10 +193,14 @@ int32_t zkb_mimc_hash_matrix_batch(zkb_ctx* ctx, const uint8_t* w, const uint8_t
                                    uint32_t n_rc, uint64_t count, uint8_t* out);
 /* device-side training trace (src/training/prover.rs:90-218 without the PCIe ingest): the caller uploads the n_raw distinct raw
  * state rows (n_raw = batch_size + 1, `half` = 120 values each); rows are [raw + mask || mask] with 64-bit masks generated on the
- * device from `seed`.  Returns the device pointer (context-owned, column-major [2*half][n]) for zkb_prove_device and the first /
+ * device.  The masks hide the raw model state (the masked first and last rows are public inputs, src/training/air.rs), so they
+ * are a ChaCha20 keystream: key32 = 32 key bytes, or NULL to draw the key from OS entropy (getrandom) — what the reference's
+ * rand::thread_rng() does (src/training/prover.rs:117-121).  Pass a key only for reproducible tests.  Mask of (row i, column j)
+ * = little-endian u64 number (j mod 8) of ChaCha20 block (i * ceil(half/8) + j div 8), nonce 0.
+ * Returns the device pointer (context-owned, column-major [2*half][n]) for zkb_prove_device and the first /
  * last trace rows (2*half elements each) that get_pub_inputs needs (src/training/prover.rs:245-246). */
-int32_t zkb_training_trace_device(zkb_ctx* ctx, const uint8_t* raw_rows, uint32_t n_raw, uint32_t half, uint64_t n, uint64_t seed,
-                                  void** d_out, uint8_t* first_row_out, uint8_t* last_row_out);
+int32_t zkb_training_trace_device(zkb_ctx* ctx, const uint8_t* raw_rows, uint32_t n_raw, uint32_t half, uint64_t n,
+                                  const uint8_t* key32, void** d_out, uint8_t* first_row_out, uint8_t* last_row_out);
 /* copy `bytes` bytes of context-owned device memory to the host (debugging / tests) */
 int32_t zkb_download(zkb_ctx* ctx, const void* d_src, uint64_t bytes, uint8_t* out);
 /* upload a column-major host trace into a context-owned device buffer (for device-resident timing) */

@@ -4,6 +4,7 @@
 #include "proof.h"
 
 using namespace orc;
+namespace orc { extern Fe* g_dump_comp_trace; }
 
 extern "C" {
 
@@ -147,5 +148,7 @@ int orc_verify(const orc_air_desc* d, const uint8_t* proof, uint64_t len, orc_tr
     } catch (const std::exception& e) { set_err(err, errlen, e.what()); return -1; }
 }
 void orc_free(void* p) { free(p); }
+// test hook: CompositionPolyTrace (ce_blowup * trace_len elements) of the next orc_prove call; pass NULL to switch it off
+void orc_dump_comp_trace(uint8_t* out) { g_dump_comp_trace = (Fe*)out; }
 
 }  // extern "C"

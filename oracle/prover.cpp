@@ -9,6 +9,8 @@
 namespace orc {
 
 int g_threads = 1;
+// test hook: when set, prove() copies the constraint evaluations over the ce domain (CompositionPolyTrace, before interpolation) here
+Fe* g_dump_comp_trace = nullptr;
 
 // RowMatrix::evaluate_polys_over: LDE of every column polynomial over 3*<w_N>, row-major [N][w]
 static std::vector<Fe> evaluate_polys_over(const std::vector<std::vector<Fe>>& polys, size_t n, size_t blowup) {
@@ -137,6 +139,7 @@ Proof prove(const Air& air, const Fe* trace_colmajor, Transcript* ts, uint64_t f
         });
     }
 
+    if (g_dump_comp_trace) memcpy(g_dump_comp_trace, comp.data(), ce_n * sizeof(Fe));
     // 3 ---- DefaultConstraintCommitment::new / CompositionPoly::new --------------------------------------
     interpolate_poly_with_offset(comp.data(), ce_n, offset);
     for (size_t i = c * n; i < ce_n; i++) if (comp[i].v != 0) { ts->comp_degree_ok = 0; break; }

@@ -106,6 +106,18 @@ def prove(air, trace_bytes, force_nonce=0):
     return proof, ts, secs.value
 
 
+def comp_trace(air, trace_bytes, ce_blowup):
+    """CompositionPolyTrace of DefaultConstraintEvaluator::evaluate (ce_blowup * n elements, natural ce-domain order), taken
+    from inside a full oracle proof.  Returns (evaluations, proof bytes, Transcript)."""
+    out = C.create_string_buffer(16 * air["trace_len"] * ce_blowup)
+    lib().orc_dump_comp_trace(out)
+    try:
+        proof, ts, _ = prove(air, trace_bytes)
+    finally:
+        lib().orc_dump_comp_trace(None)
+    return out.raw, proof, ts
+
+
 def verify(air, proof):
     d = make_desc(air)
     ts = Transcript()

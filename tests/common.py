@@ -73,3 +73,30 @@ def transcript_diff(a, b):
         if xb != yb:
             return f
     return None
+
+
+def chacha20_block(key, counter):
+    """ChaCha20 block function (20 rounds, 64-bit block counter in words 12-13, zero nonce): the device-side mask generator of
+    zkb_training_trace_device restated for the tests.  Returns 64 keystream bytes."""
+    import struct
+    m = 0xFFFFFFFF
+    rotl = lambda v, c: ((v << c) & m) | (v >> (32 - c))
+    x = [0x61707865, 0x3320646E, 0x79622D32, 0x6B206574] + list(struct.unpack("<8I", key)) + [counter & m, (counter >> 32) & m, 0, 0]
+    s = list(x)
+
+    def qr(a, b, c, d):
+        x[a] = (x[a] + x[b]) & m; x[d] = rotl(x[d] ^ x[a], 16)
+        x[c] = (x[c] + x[d]) & m; x[b] = rotl(x[b] ^ x[c], 12)
+        x[a] = (x[a] + x[b]) & m; x[d] = rotl(x[d] ^ x[a], 8)
+        x[c] = (x[c] + x[d]) & m; x[b] = rotl(x[b] ^ x[c], 7)
+    for _ in range(10):
+        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
+        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
+    return struct.pack("<16I", *[(a + b) & m for a, b in zip(x, s)])
+
+
+def training_mask(key, row, col, half):
+    """Mask of trace cell (row, col) as zkb_training_trace_device generates it (include/zkb200.h)."""
+    blocks = (half + 7) // 8
+    ks = chacha20_block(key, row * blocks + col // 8)
+    return int.from_bytes(ks[8 * (col % 8):8 * (col % 8) + 8], "little")

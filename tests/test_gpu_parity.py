@@ -370,25 +370,19 @@ def test_randomized_shape_sweep(gpu_ctx, oracle):
 
 
 def test_device_side_training_trace(gpu_ctx, oracle):
-    """the training trace built on the GPU equals its host reconstruction (same raw states, same counter-based
-    masks) and proves / verifies like a host-built one."""
+    """the training trace built on the GPU equals its host reconstruction (same raw states, same ChaCha20 mask
+    stream under the test's key) and proves / verifies like a host-built one; without a key the masks come from OS entropy."""
     p = T.training_prover(3, T.options())
-    seed = 0xC0FFEE
-    dt = p.build_trace_device(seed=seed, ctx=gpu_ctx)
+    key = bytes(range(32))
+    dt = p.build_trace_device(key=key, ctx=gpu_ctx)
     assert (dt.width(), dt.length()) == (240, 512)
     host = dt.to_host()
-
-    def splitmix(x):
-        x = (x + 0x9E3779B97F4A7C15) & (2**64 - 1)
-        x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & (2**64 - 1)
-        x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & (2**64 - 1)
-        return x ^ (x >> 31)
     states = p.raw_states()
     assert len(states) == 4
     for i in (0, 1, 2, 3, 4, 100, 511):
         raw = states[min(i, 3)]
-        for j in (0, 1, 57, 119):
-            mask = splitmix(seed ^ splitmix((i * 0x100000001B3 + j) & (2**64 - 1)))
+        for j in (0, 1, 7, 8, 57, 119):
+            mask = T.training_mask(key, i, j, 120)
             assert host.get(120 + j, i) == mask and host.get(j, i) == (raw[j] + mask) % P
     assert [dt.get(c, 0) for c in range(240)] == [host.get(c, 0) for c in range(240)]
     assert [dt.get(c, 511) for c in range(240)] == [host.get(c, 511) for c in range(240)]
@@ -397,6 +391,11 @@ def test_device_side_training_trace(gpu_ctx, oracle):
     assert Z.verify(proof, air)
     oracle.verify(air, proof.to_bytes())
     assert proof.to_bytes() == oracle.prove(air, host.to_bytes())[0]
+    # default: a fresh OS-entropy key per call - two traces must not share their masks
+    a = p.build_trace_device(ctx=gpu_ctx).to_host()
+    b = p.build_trace_device(ctx=gpu_ctx).to_host()
+    assert not np.array_equal(a.data[120:], b.data[120:])
+    assert np.all(a.data[120:, :, 1] == 0)  # 64-bit masks (src/training/prover.rs:119-121)
 
 
 def test_boundary_polynomial_path_forced():

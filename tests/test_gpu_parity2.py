@@ -1,0 +1,191 @@
+"""GPU parity tests, part 2 (round 2): every BASELINE.json configuration at its exact size, the values the three Winterfell
+associated types return through the C ABI (TraceLde / ConstraintEvaluator / ConstraintCommitment), and error paths added
+in round 2.  Everything goes through libzkb200.so; the oracle is only the checker."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+import zk_stark_project_b200 as Z
+from zk_stark_project_b200 import lib as L
+from zk_stark_project_b200.verifier import _Reader
+from tests import common as T
+
+pytestmark = pytest.mark.gpu
+P = Z.P
+
+
+def _mimc_case(ctx, oracle, w, n, opts, check_trace=True):
+    rc = Z.get_round_constants()
+    seeds = [j + 1 for j in range(w)]
+    raw = ctx.mimc_trace(seeds, n, rc)
+    if check_trace:
+        assert raw == oracle.mimc_trace(seeds, n, rc), "device-side MiMC trace differs from the oracle's"
+    data = np.frombuffer(raw, dtype=np.uint64).reshape(w, n, 2)
+    get = lambda c, r: int(data[c, r, 0]) | (int(data[c, r, 1]) << 64)
+    air = Z.MimcAir(w, n, Z.MimcInputs([get(j, 0) for j in range(w)], [get(j, n - 1) for j in range(w)]), opts).describe()
+    return air, data
+
+
+def _parity(ctx, oracle, air, data):
+    proof, ts = ctx.prove_host(air, np.ascontiguousarray(data).ctypes.data)
+    ref, ts_o, _ = oracle.prove(air, data.tobytes())
+    assert T.transcript_diff(ts_o, ts) is None, f"transcripts diverge at `{T.transcript_diff(ts_o, ts)}`"
+    assert proof == ref
+    oracle.verify(air, proof)
+    return proof
+
+
+def test_config0_mimc_2p14_exact(gpu_ctx, oracle):
+    """BASELINE.json configs[0] exactly: MiMC 64 chains x 2^14 steps, blowup 8, the reference's other options
+    (40 queries, 21-bit grinding, FRI folding 16, remainder degree <= 7; src/main.rs:98-107)."""
+    air, data = _mimc_case(gpu_ctx, oracle, 64, 1 << 14, Z.ProofOptions(40, 8, 21, Z.FieldExtension.NONE, 16, 7))
+    proof = _parity(gpu_ctx, oracle, air, data)
+    assert Z.verify(proof, air)
+
+
+def test_mimc_2p20_parity(gpu_ctx, oracle):
+    """The headline shape (BASELINE.json metric: 2^20-row trace; configs[4] lower end): MiMC 64 x 2^20, blowup 8 (LDE 8 GiB),
+    reference options — byte-identical to the oracle (three NTT passes, boundary-polynomial path, five FRI layers)."""
+    air, data = _mimc_case(gpu_ctx, oracle, 64, 1 << 20, Z.ProofOptions(40, 8, 21, Z.FieldExtension.NONE, 16, 7))
+    _parity(gpu_ctx, oracle, air, data)
+
+
+def _parse_queries(proof, w, c):
+    """trace / constraint Queries sections of Proof::to_bytes() (rows bytes, BatchMerkleProof bytes)."""
+    r = _Reader(proof)
+    r.take(4 + 2 + 1 + 16 + 8 + 2)
+    r.u8()
+    r.take(r.uint(2))
+    t_rows, t_paths = r.take(r.usize()), r.take(r.usize())
+    c_rows, c_paths = r.take(r.usize()), r.take(r.usize())
+    return t_rows, t_paths, c_rows, c_paths
+
+
+def _staged_values(ctx, oracle, air, data, ce):
+    """What the Rust associated types would hand to Winterfell: trace polynomials (TracePolyTable), main-trace frames
+    (read_main_trace_frame_into) incl. the wrap-around rows, CompositionPolyTrace, and both Queries."""
+    lib, h = ctx.lib, ctx.handle
+    w, n, beta = air["trace_width"], air["trace_len"], air["options"]["blowup"]
+    N = n * beta
+    d = L.make_desc(air)
+    buf = np.ascontiguousarray(data)
+    cols = (C.c_void_p * w)(*[buf.ctypes.data + j * n * 16 for j in range(w)])
+    comp, ref_proof, ts = oracle.comp_trace(air, buf.tobytes(), ce)
+    _, lde, polys = oracle.trace_commit(buf.tobytes(), n, w, beta, want_lde=True, want_polys=True)
+    root = C.create_string_buffer(32)
+    ctx.check(lib.zkb_begin(h, C.byref(d)))
+    ctx.check(lib.zkb_trace_commit(h, cols, root))
+    assert root.raw == bytes(ts.trace_root)
+    # TracePolyTable: row-major [n][w] on our side, column-major [w][n] in the oracle
+    out = C.create_string_buffer(16 * n * w)
+    ctx.check(lib.zkb_trace_polys_read(h, out))
+    got = np.frombuffer(out.raw, dtype=np.uint64).reshape(n, w, 2).transpose(1, 0, 2)
+    assert np.array_equal(got, np.frombuffer(polys, dtype=np.uint64).reshape(w, n, 2)), "trace polynomials differ"
+    # frames: first, last blowup rows (next wraps to the start), and random steps
+    rng = random.Random(N + w)
+    steps = [0, 1, beta, N - 1, N - beta, N - beta - 1, N - beta + 1] + [rng.randrange(N) for _ in range(24)]
+    cur, nxt = C.create_string_buffer(16 * w), C.create_string_buffer(16 * w)
+    row = lambda r: lde[r * 16 * w:(r + 1) * 16 * w]
+    for s in steps:
+        ctx.check(lib.zkb_trace_read_frame(h, C.c_uint64(s), cur, nxt))
+        assert cur.raw == row(s) and nxt.raw == row((s + beta) % N), f"frame at LDE step {s} differs"
+    assert lib.zkb_trace_read_frame(h, C.c_uint64(N), cur, nxt) == -1  # out of range
+    # batched frame read: the same rows in one call
+    k = len(steps)
+    arr = (C.c_uint64 * k)(*steps)
+    cur_b, nxt_b = C.create_string_buffer(16 * w * k), C.create_string_buffer(16 * w * k)
+    ctx.check(lib.zkb_trace_read_frames(h, arr, C.c_uint32(k), cur_b, nxt_b))
+    for i, s in enumerate(steps):
+        assert cur_b.raw[i * 16 * w:(i + 1) * 16 * w] == row(s) and nxt_b.raw[i * 16 * w:(i + 1) * 16 * w] == row((s + beta) % N)
+    # ConstraintEvaluator::evaluate -> CompositionPolyTrace
+    ev = C.create_string_buffer(16 * n * ce)
+    ctx.check(lib.zkb_constraints_eval(h, bytes(ts.constraint_alpha), ev))
+    assert ev.raw == comp, "constraint evaluations differ"
+    ctx.check(lib.zkb_constraints_commit(h, root))
+    assert root.raw == bytes(ts.constraint_root)
+    ctx.check(lib.zkb_ood_eval(h, bytes(ts.z), None, None, None))
+    ctx.check(lib.zkb_deep_compose(h, bytes(ts.deep_alpha)))
+    nl = C.c_uint32()
+    ctx.check(lib.zkb_fri_num_layers(h, C.byref(nl)))
+    for l in range(nl.value):
+        ctx.check(lib.zkb_fri_commit_layer(h, root))
+        assert root.raw == bytes(ts.fri_roots[l])
+        ctx.check(lib.zkb_fri_fold(h, bytes(ts.fri_alphas[l])))
+    rem, cnt = C.create_string_buffer(16 * 256), C.c_uint64()
+    ctx.check(lib.zkb_fri_remainder(h, rem, C.byref(cnt), root))
+    assert root.raw == bytes(ts.remainder_commitment)
+    # TraceLde::query / ConstraintCommitment::query against the Queries sections of the oracle's proof
+    c = 6 if air["air_id"] == 3 else 1
+    t_rows, t_paths, c_rows, c_paths = _parse_queries(ref_proof, w, c)
+    pos = (C.c_uint32 * ts.n_positions)(*list(ts.positions)[:ts.n_positions])
+    for which, width, want_rows, want_paths in ((0, w, t_rows, t_paths), (1, c, c_rows, c_paths)):
+        rows = C.create_string_buffer(16 * width * ts.n_positions)
+        po, ln = C.c_void_p(), C.c_uint64()
+        ctx.check(lib.zkb_query(h, C.c_uint32(which), pos, C.c_uint32(ts.n_positions), rows, C.byref(po), C.byref(ln)))
+        paths = C.string_at(po, ln.value)
+        lib.zkb_free(po)
+        assert rows.raw == want_rows, f"queried rows of commitment {which} differ"
+        assert paths == want_paths, f"batch Merkle proof of commitment {which} differs"
+
+
+def test_staged_values_aggregation(gpu_ctx, oracle):
+    """BASELINE.json configs[2] (FedAvg over 16 updates, reference options) through the staged surface."""
+    p = T.aggregation_prover(16, Z.ProofOptions.reference())
+    trace = p.build_trace()
+    _staged_values(gpu_ctx, oracle, p.describe(trace), np.ascontiguousarray(trace.data), 2)
+
+
+def test_staged_values_training_2p16(gpu_ctx, oracle):
+    """BASELINE.json configs[1] (2^16 x 240, reference options) through the staged surface."""
+    n = 1 << 16
+    data = T.random_felts(240 * n, 0x5EED0002).reshape(240, n, 2)
+    air = T.synthetic_training_air(n, Z.ProofOptions.reference(), data)
+    _staged_values(gpu_ctx, oracle, air, data, 2)
+
+
+def test_staged_values_mimc(gpu_ctx, oracle):
+    """MiMC (ce = beta = 8, six composition columns) through the staged surface, two NTT passes."""
+    air, data = _mimc_case(gpu_ctx, oracle, 16, 1 << 12, T.options(blowup=8))
+    _staged_values(gpu_ctx, oracle, air, data, 8)
+
+
+def test_non_canonical_trace_is_reduced(gpu_ctx, oracle):
+    """Winterfell's BaseElement::new reduces a u128 >= p; trace cells handed over as raw u128 in [p, 2^128) must give the same
+    proof as their canonical representatives (canonicalise on ingest)."""
+    p = T.mimc_prover(4, 256, T.options(blowup=8))
+    trace = p.build_trace()
+    air = p.describe(trace)
+    data = np.ascontiguousarray(trace.data).copy()
+    ref, _ = gpu_ctx.prove_host(air, data.ctypes.data)
+    # cells small enough that v + p < 2^128: the seeds in row 0 (and any other small cell)
+    bumped = 0
+    for j in range(4):
+        for i in range(256):
+            v = int(data[j, i, 0]) | (int(data[j, i, 1]) << 64)
+            if v + P < 2**128:
+                v += P
+                data[j, i, 0], data[j, i, 1] = v & (2**64 - 1), v >> 64
+                bumped += 1
+    assert bumped >= 4
+    got, _ = gpu_ctx.prove_host(air, data.ctypes.data)
+    assert got == ref
+    assert ref == oracle.prove(air, trace.to_bytes())[0]
+
+
+def test_invalid_trace_reports_degree_failure(gpu_ctx, oracle):
+    """A trace that violates the AIR: the composition polynomial does not fit its c*n coefficients.  The oracle flags it in the
+    transcript (comp_degree_ok = 0); the library must do the same instead of silently truncating."""
+    p = T.mimc_prover(2, 128, T.options(blowup=8))
+    trace = p.build_trace()
+    air = p.describe(trace)
+    data = np.ascontiguousarray(trace.data).copy()
+    data[1, 77, 0] ^= 1  # break one transition
+    _, ts_o, _ = oracle.prove(air, data.tobytes())
+    assert ts_o.comp_degree_ok == 0
+    _, ts = gpu_ctx.prove_host(air, data.ctypes.data)
+    assert ts.comp_degree_ok == 0
+    # and a valid trace keeps the flag set
+    _, ts = gpu_ctx.prove_host(air, np.ascontiguousarray(trace.data).ctypes.data)
+    assert ts.comp_degree_ok == 1

@@ -163,3 +163,13 @@ def test_device_field_constants_in_source():
         else:
             exp = ((e[base] if base != "r" else exp) << int(sh)) + e[mul]
     assert exp == P - 2
+
+
+def test_chacha20_block_known_answer():
+    """The tests' restatement of the device-side mask generator against the published ChaCha20 keystream for the all-zero key
+    and nonce (block 0), so that the GPU comparison in test_device_side_training_trace pins the device code to real ChaCha20."""
+    from tests import common as T
+    ks = T.chacha20_block(bytes(32), 0)
+    assert ks.hex() == ("76b8e0ada0f13d90405d6ae55386bd28bdd219b8a08ded1aa836efcc8b770dc7"
+                        "da41597c5157488d7724e03fb8d84a376a43b8f41518a11cc387b669b2ee6586")
+    assert T.chacha20_block(bytes(32), 1).hex().startswith("9f07e7be5551387a98ba977c732d080d")

@@ -61,13 +61,17 @@ __device__ __forceinline__ size_t lde_addr(const LdeMat& m, uint32_t k, uint32_t
 
 // ------------------------------------------------------------------------------------------------
 // transpose: `wc` columns of a column-major matrix (column length n) -> columns [0, wc) of a row-major matrix
-// with row stride `out_stride`   (first step of K1; called per column group)
+// with row stride `out_stride`   (first step of K1; called per column group).  This is where caller data enters the field
+// arithmetic: a raw u128 in [p, 2^128) is reduced here, as winter-math's BaseElement::new does (one add-and-select per cell).
 __global__ void k_transpose_cols(const fe* __restrict__ in, fe* __restrict__ out, uint32_t n, uint32_t wc, uint32_t out_stride) {
     __shared__ uint4 tile[32][33];
     const uint32_t i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
     for (uint32_t jj = threadIdx.y; jj < 32; jj += blockDim.y) {
         uint32_t j = j0 + jj, i = i0 + threadIdx.x;
-        if (j < wc && i < n) tile[jj][threadIdx.x] = reinterpret_cast<const uint4*>(in)[(size_t)j * n + i];
+        if (j < wc && i < n) {
+            const fe v = fe_canon(fe_load(in + (size_t)j * n + i), 0);
+            tile[jj][threadIdx.x] = make_uint4(v.x[0], v.x[1], v.x[2], v.x[3]);
+        }
     }
     __syncthreads();
     for (uint32_t ii = threadIdx.y; ii < 32; ii += blockDim.y) {
@@ -264,12 +268,15 @@ __global__ void __launch_bounds__(256, 3) k_ntt_pass(const NttPass p) {
     }
 }
 
-// x[m] *= scale * base^m   (interpolate_poly_with_offset: base = 1/offset)
-__global__ void k_scale_pow(fe* x, uint64_t n, PowTab base, fe scale) {
+// x[m] *= scale * base^m   (interpolate_poly_with_offset: base = 1/offset).  Coefficients at m >= keep are dropped by the caller
+// (CompositionPoly::new keeps c*n of the ce*n); a non-zero one means the trace violates the AIR: *bad_degree is raised.
+__global__ void k_scale_pow(fe* x, uint64_t n, PowTab base, fe scale, uint64_t keep, uint32_t* __restrict__ bad_degree) {
     uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= n) return;
+    const fe v = fe_load(x + m);
+    if (m >= keep) { if (!fe_is_zero(v)) atomicOr(bad_degree, 1u); return; }
     fe f = fe_mul(powtab(base, (uint32_t)m), scale);
-    fe_store(x + m, fe_mul(fe_load(x + m), f));
+    fe_store(x + m, fe_mul(v, f));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -775,10 +782,10 @@ __global__ void k_deep_add_h(fe* __restrict__ ab, uint32_t n, const fe* __restri
 __global__ void k_mimc_trace(const fe* __restrict__ seeds, uint32_t w, uint64_t n, const fe* __restrict__ rc, uint32_t L, fe* __restrict__ out) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= w) return;
-    fe x = fe_load(seeds + j);
+    fe x = fe_canon(fe_load(seeds + j), 0);
     for (uint64_t i = 0; i < n; i++) {
         fe_store(out + (size_t)j * n + i, x);
-        fe a1 = fe_add(x, fe_ldg(rc + (i & (L - 1))));
+        fe a1 = fe_add(x, fe_canon(fe_ldg(rc + (i & (L - 1))), 0));
         fe a2 = fe_sqr(a1), a4 = fe_sqr(a2), a6 = fe_mul(a4, a2);
         x = fe_mul(a6, a1);
     }
@@ -787,23 +794,44 @@ __global__ void k_mimc_trace(const fe* __restrict__ seeds, uint32_t w, uint64_t 
 // device-side training trace (src/training/prover.rs:117-130,188-199): row i = [raw_i + mask_i || mask_i] with
 // a fresh 64-bit mask per cell.  The raw state only changes during the first `n_raw - 1` steps (the batch), afterwards it is
 // constant (src/training/prover.rs:185), so the caller uploads n_raw rows of `half` raw values and the masks are generated
-// here with a counter-based generator (splitmix64 of (seed, row, column)); the reference draws them from an unseeded
-// thread_rng, so any generator is equally faithful.  Output: column-major [2*half][n].
-__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
-    x += 0x9E3779B97F4A7C15ull;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-    return x ^ (x >> 31);
+// here.  The masks are the only thing hiding the raw model state (masked rows 0 and n-1 are public inputs), and the
+// reference draws them from rand::thread_rng(), an OS-seeded ChaCha CSPRNG: so do we — ChaCha20 keystream under a 256-bit
+// key (drawn from OS entropy by the host unless the caller passes one), block counter = row * blocks_per_row + column block,
+// eight 64-bit masks per 64-byte block.  Output: column-major [2*half][n].
+__device__ __forceinline__ void chacha20_block(const uint32_t key[8], uint64_t counter, uint32_t out[16]) {
+    uint32_t x[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7],
+                      (uint32_t)counter, (uint32_t)(counter >> 32), 0u, 0u};
+    uint32_t s[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = x[i];
+#define ZKB_QR(a, b, c, d)                                                                     \
+    x[a] += x[b]; x[d] = __funnelshift_l(x[d] ^ x[a], x[d] ^ x[a], 16); x[c] += x[d]; x[b] = __funnelshift_l(x[b] ^ x[c], x[b] ^ x[c], 12); \
+    x[a] += x[b]; x[d] = __funnelshift_l(x[d] ^ x[a], x[d] ^ x[a], 8);  x[c] += x[d]; x[b] = __funnelshift_l(x[b] ^ x[c], x[b] ^ x[c], 7);
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        ZKB_QR(0, 4, 8, 12) ZKB_QR(1, 5, 9, 13) ZKB_QR(2, 6, 10, 14) ZKB_QR(3, 7, 11, 15)
+        ZKB_QR(0, 5, 10, 15) ZKB_QR(1, 6, 11, 12) ZKB_QR(2, 7, 8, 13) ZKB_QR(3, 4, 9, 14)
+    }
+#undef ZKB_QR
+#pragma unroll
+    for (int i = 0; i < 16; i++) out[i] = x[i] + s[i];
 }
-__global__ void k_training_trace(const fe* __restrict__ raw, uint32_t n_raw, uint32_t half, uint64_t n, uint64_t seed, fe* __restrict__ out) {
+struct ChaChaKey { uint32_t k[8]; };
+__global__ void k_training_trace(const fe* __restrict__ raw, uint32_t n_raw, uint32_t half, uint64_t n, const ChaChaKey key, fe* __restrict__ out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t j = blockIdx.y;
+    const uint32_t jb = blockIdx.y, nb = gridDim.y;   // column block: masks of columns [8 jb, 8 jb + 8)
     if (i >= n) return;
-    const uint64_t m = splitmix64(seed ^ splitmix64(i * 0x100000001B3ull + j));
-    const fe mask = fe_from_u64(m);
+    uint32_t ks[16];
+    chacha20_block(key.k, i * nb + jb, ks);
     const uint64_t r = i < n_raw ? i : (uint64_t)n_raw - 1;
-    fe_store(out + (size_t)j * n + i, fe_add(fe_load(raw + r * half + j), mask));
-    fe_store(out + (size_t)(half + j) * n + i, mask);
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const uint32_t j = jb * 8 + q;
+        if (j >= half) break;
+        fe mask; mask.x[0] = ks[2 * q]; mask.x[1] = ks[2 * q + 1]; mask.x[2] = mask.x[3] = 0;
+        fe_store(out + (size_t)j * n + i, fe_add(fe_canon(fe_load(raw + r * half + j), 0), mask));
+        fe_store(out + (size_t)(half + j) * n + i, mask);
+    }
 }
 // read two rows of a column-major device trace (boundary rows for get_pub_inputs)
 __global__ void k_read_rows(const fe* __restrict__ trace, uint32_t w, uint64_t n, uint64_t r0, uint64_t r1, fe* __restrict__ out) {
@@ -827,7 +855,7 @@ __device__ __forceinline__ fe mimc_cipher_dev(fe inp, const fe rc, const fe z) {
 __global__ void k_mimc_cipher_batch(const fe* __restrict__ x, const fe* __restrict__ rc, const fe* __restrict__ z, uint64_t n, fe* __restrict__ out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    fe_store(out + i, mimc_cipher_dev(fe_load(x + i), fe_load(rc + i), fe_load(z + i)));
+    fe_store(out + i, mimc_cipher_dev(fe_canon(fe_load(x + i), 0), fe_canon(fe_load(rc + i), 0), fe_canon(fe_load(z + i), 0)));
 }
 // w: [count][ac][fe], b: [count][ac]
 __global__ void k_mimc_hash_matrix_batch(const fe* __restrict__ w, const fe* __restrict__ b, uint32_t ac, uint32_t fe_n, const fe* __restrict__ rc,
@@ -836,8 +864,8 @@ __global__ void k_mimc_hash_matrix_batch(const fe* __restrict__ w, const fe* __r
     if (t >= count) return;
     fe z = fe_zero();
     for (uint32_t i = 0; i < ac; i++) {
-        for (uint32_t j = 0; j < fe_n; j++) z = mimc_cipher_dev(fe_load(w + (t * ac + i) * fe_n + j), fe_ldg(rc + j % n_rc), z);
-        z = mimc_cipher_dev(fe_load(b + t * ac + i), fe_ldg(rc + i % n_rc), z);
+        for (uint32_t j = 0; j < fe_n; j++) z = mimc_cipher_dev(fe_canon(fe_load(w + (t * ac + i) * fe_n + j), 0), fe_canon(fe_ldg(rc + j % n_rc), 0), z);
+        z = mimc_cipher_dev(fe_canon(fe_load(b + t * ac + i), 0), fe_canon(fe_ldg(rc + i % n_rc), 0), z);
     }
     fe_store(out + t, z);
 }

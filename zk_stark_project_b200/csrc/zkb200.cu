@@ -8,6 +8,7 @@
 // There is no CPU fallback: without a CUDA device every entry point fails.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sys/random.h>
 #include <nccl.h>
 #include <cstdio>
 #include <cstdlib>
@@ -88,7 +89,7 @@ struct zkb_ctx {
 
     // ---- device memory (grown on demand, reused between proofs) ----------------------------------------------
     DevBuf d_trace, d_bufA, d_bufB, d_tmp1, d_tmp2, d_lde, d_tree, d_small, d_comp_evals, d_comp_lde, d_comp_tree, d_ab, d_ab_lde,
-        d_deep, d_roots_lo, d_roots_hi, d_inv3_lo, d_inv3_hi, d_pow3, d_aux, d_gather, d_user_trace;
+        d_deep, d_roots_lo, d_roots_hi, d_inv3_lo, d_inv3_hi, d_pow3, d_aux, d_gather, d_user_trace, d_flags;
     std::vector<DevBuf> d_fri_evals, d_fri_tree;
     fe* d_polys = nullptr;  // points into bufA or bufB
     uint32_t lde_log_p = 0, comp_log_p = 0, ab_log_p = 0;
@@ -177,7 +178,7 @@ struct zkb_ctx {
         cudaSetDevice(device);
         cudaStreamSynchronize(stream);
         for (DevBuf* b : {&d_trace, &d_bufA, &d_bufB, &d_tmp1, &d_tmp2, &d_lde, &d_tree, &d_small, &d_comp_evals, &d_comp_lde, &d_comp_tree,
-                          &d_ab, &d_ab_lde, &d_deep, &d_roots_lo, &d_roots_hi, &d_inv3_lo, &d_inv3_hi, &d_pow3, &d_aux, &d_gather, &d_user_trace,
+                          &d_ab, &d_ab_lde, &d_deep, &d_roots_lo, &d_roots_hi, &d_inv3_lo, &d_inv3_hi, &d_pow3, &d_aux, &d_gather, &d_user_trace, &d_flags,
                           &d_lde_rows, &d_mg_a, &d_mg_b, &d_bnd_coef, &d_bnd_lde})
             b->release();
         if (comm) { g_nccl.CommDestroy(comm); comm = nullptr; }
@@ -788,7 +789,11 @@ struct zkb_ctx {
             Xform x{d_comp_evals.as<fe>(), 1, 0, coef, 1, 0, 1, log_n + log_ce, true, false, 0, false, HF()};
             run_xform(x, d_tmp1, d_tmp2);
             // inv3tab covers exponents < 2^log_N >= ce*n
-            k_scale_pow<<<(unsigned)((cen + 255) / 256), 256, 0, stream>>>(coef, cen, inv3tab, to_fe(HF::from_u64(cen).inv()));
+            // the c*n kept coefficients are scaled; the dropped tail must be zero, else the trace violates the AIR (flag in d_flags)
+            d_flags.ensure(256);
+            CK(cudaMemsetAsync(d_flags.p, 0, 4, stream));
+            k_scale_pow<<<(unsigned)((cen + 255) / 256), 256, 0, stream>>>(coef, cen, inv3tab, to_fe(HF::from_u64(cen).inv()), (uint64_t)c * n,
+                                                                            d_flags.as<uint32_t>());
             check_launch();
         }
         // evaluate the c column polynomials over the LDE domain (panel layout, width c)
@@ -820,7 +825,11 @@ struct zkb_ctx {
         build_merkle(d_comp_tree.as<uint32_t>(), N);
         t_end(TS_COMP);
         Digest32 root;
+        uint32_t bad_degree = 0;
+        CK(cudaMemcpyAsync(&bad_degree, d_flags.p, 4, cudaMemcpyDeviceToHost, stream));
         d2h(root.b, d_comp_tree.as<uint32_t>() + 8, 32);
+        // as the oracle (and a release build of Winterfell) the proof is still produced; it will not verify
+        if (bad_degree) ts.comp_degree_ok = 0;
         parts.commitments.push_back(root);
         memcpy(ts.constraint_root, root.b, 32);
         if (root_out) memcpy(root_out, root.b, 32);
@@ -1339,22 +1348,38 @@ int32_t zkb_trace_commit(zkb_ctx* ctx, const uint8_t* const* cols, uint8_t root_
 int32_t zkb_trace_commit_device(zkb_ctx* ctx, const void* d, uint8_t root_out[32]) {
     return guarded(ctx, [&] { if (!d) throw InvalidArg("null device trace"); ctx->trace_commit_device((const fe*)d, root_out); });
 }
-int32_t zkb_trace_read_frame(zkb_ctx* ctx, uint64_t lde_step, uint8_t* cur, uint8_t* nxt) {
+// TraceLde::read_main_trace_frame_into for `count` LDE steps at once: one upload of the row indices, one gather launch, one
+// download (the single-step call is the count = 1 case).  An evaluator that walks the whole domain should ask for thousands
+// of steps per call — or, better, not read frames at all and use zkb_constraints_eval.
+int32_t zkb_trace_read_frames(zkb_ctx* ctx, const uint64_t* lde_steps, uint32_t count, uint8_t* cur, uint8_t* nxt) {
     return guarded(ctx, [&] {
-        if (ctx->stage < ST_TRACE) throw StateError("zkb_trace_read_frame: trace is not committed");
+        if (ctx->stage < ST_TRACE) throw StateError("zkb_trace_read_frames: trace is not committed");
+        if (ctx->mg_active) throw StateError("zkb_trace_read_frames: not available for a column-sharded trace");
         const uint64_t N = ctx->air.lde_size();
-        if (lde_step >= N || !cur || !nxt) throw InvalidArg("bad frame request");
-        std::vector<uint32_t> pos{(uint32_t)lde_step, (uint32_t)((lde_step + ctx->air.blowup) % N)};
+        if (!lde_steps || !cur || !nxt) throw InvalidArg("bad frame request");
+        if (count == 0) return;
+        if (count > (1u << 20)) throw InvalidArg("at most 2^20 frames per call");
+        std::vector<uint32_t> pos(2 * (size_t)count);
+        for (uint32_t q = 0; q < count; q++) {
+            if (lde_steps[q] >= N) throw InvalidArg("LDE step out of range");
+            pos[q] = (uint32_t)lde_steps[q];
+            pos[count + q] = (uint32_t)((lde_steps[q] + ctx->air.blowup) % N);   // frame.next wraps around the LDE domain
+        }
+        CK(cudaSetDevice(ctx->device));
         const uint32_t w = ctx->air.w;
-        ctx->d_gather.ensure(1024 + 2 * (size_t)w * 16);
+        const size_t o_rows = ((pos.size() * 4 + 255) / 256) * 256, row_bytes = (size_t)count * w * 16;
+        ctx->d_gather.ensure(o_rows + 2 * row_bytes);
         uint8_t* base = ctx->d_gather.as<uint8_t>();
-        ctx->h2d(base, pos.data(), 8);
-        k_gather_lde_rows<<<(2 * w + 127) / 128, 128, 0, ctx->stream>>>(ctx->lde_mat(), (const uint32_t*)base, 2, (fe*)(base + 1024));
+        ctx->h2d(base, pos.data(), pos.size() * 4);
+        const uint64_t th = 2 * (uint64_t)count * w;
+        k_gather_lde_rows<<<(unsigned)((th + 127) / 128), 128, 0, ctx->stream>>>(ctx->lde_mat(), (const uint32_t*)base, 2 * count, (fe*)(base + o_rows));
         ctx->check_launch();
-        std::vector<uint8_t> h(2 * (size_t)w * 16);
-        ctx->d2h(h.data(), base + 1024, h.size());
-        memcpy(cur, h.data(), (size_t)w * 16); memcpy(nxt, h.data() + (size_t)w * 16, (size_t)w * 16);
+        CK(cudaMemcpyAsync(cur, base + o_rows, row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h(nxt, base + o_rows + row_bytes, row_bytes);
     });
+}
+int32_t zkb_trace_read_frame(zkb_ctx* ctx, uint64_t lde_step, uint8_t* cur, uint8_t* nxt) {
+    return zkb_trace_read_frames(ctx, &lde_step, 1, cur, nxt);
 }
 int32_t zkb_trace_polys_read(zkb_ctx* ctx, uint8_t* out) {
     return guarded(ctx, [&] {
@@ -1501,7 +1526,7 @@ int32_t zkb_mimc_hash_matrix_batch(zkb_ctx* ctx, const uint8_t* w, const uint8_t
         ctx->d2h(out, base + count * per + n_rc, count * 16);
     });
 }
-int32_t zkb_training_trace_device(zkb_ctx* ctx, const uint8_t* raw_rows, uint32_t n_raw, uint32_t half, uint64_t n, uint64_t seed,
+int32_t zkb_training_trace_device(zkb_ctx* ctx, const uint8_t* raw_rows, uint32_t n_raw, uint32_t half, uint64_t n, const uint8_t* key32,
                                   void** d_out, uint8_t* first_row_out, uint8_t* last_row_out) {
     return guarded(ctx, [&] {
         if (!raw_rows || !d_out || n_raw == 0 || half == 0 || half > 127 || n < n_raw) throw InvalidArg("bad training trace request");
@@ -1511,8 +1536,19 @@ int32_t zkb_training_trace_device(zkb_ctx* ctx, const uint8_t* raw_rows, uint32_
         ctx->d_aux.ensure(((size_t)n_raw * half + 2 * w) * 16);
         fe* d_raw = ctx->d_aux.as<fe>();
         ctx->h2d(d_raw, raw_rows, (size_t)n_raw * half * 16);
-        dim3 grid((unsigned)((n + 255) / 256), half);
-        k_training_trace<<<grid, 256, 0, ctx->stream>>>(d_raw, n_raw, half, n, seed, ctx->d_user_trace.as<fe>());
+        // mask key: the caller's (tests, reproducible runs) or 256 bits of OS entropy, as rand::thread_rng() is seeded
+        ChaChaKey key;
+        if (key32) memcpy(key.k, key32, 32);
+        else {
+            size_t got = 0;
+            while (got < 32) {
+                const ssize_t r = getrandom((uint8_t*)key.k + got, 32 - got, 0);
+                if (r <= 0) throw std::runtime_error("getrandom failed: no entropy for the blinding masks");
+                got += (size_t)r;
+            }
+        }
+        dim3 grid((unsigned)((n + 255) / 256), (half + 7) / 8);
+        k_training_trace<<<grid, 256, 0, ctx->stream>>>(d_raw, n_raw, half, n, key, ctx->d_user_trace.as<fe>());
         ctx->check_launch();
         fe* d_rows = d_raw + (size_t)n_raw * half;
         k_read_rows<<<(w + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_user_trace.as<fe>(), w, n, 0, n - 1, d_rows);

@@ -75,7 +75,7 @@ def load():
 EXPORTS = [
     "zkb_ctx_create", "zkb_ctx_create_lane", "zkb_ctx_destroy", "zkb_last_error", "zkb_kernel_launches", "zkb_last_stage_times", "zkb_host_alloc",
     "zkb_host_free", "zkb_prove", "zkb_prove_device", "zkb_free", "zkb_begin", "zkb_trace_commit", "zkb_trace_commit_device",
-    "zkb_trace_read_frame", "zkb_trace_polys_read", "zkb_constraints_eval", "zkb_constraints_commit", "zkb_ood_eval",
+    "zkb_trace_read_frame", "zkb_trace_read_frames", "zkb_trace_polys_read", "zkb_constraints_eval", "zkb_constraints_commit", "zkb_ood_eval",
     "zkb_deep_compose", "zkb_fri_num_layers", "zkb_fri_commit_layer", "zkb_fri_fold", "zkb_fri_remainder", "zkb_grind",
     "zkb_query", "zkb_mg_unique_id", "zkb_mg_init", "zkb_mg_prove", "zkb_mg_prove_device", "zkb_prove_batch", "zkb_mimc_trace", "zkb_mimc_trace_device", "zkb_training_trace_device", "zkb_download", "zkb_blake3_host", "zkb_mimc_cipher_batch", "zkb_mimc_hash_matrix_batch", "zkb_upload_trace", "zkb_test_field", "zkb_test_hash_elements",
     "zkb_test_merkle_root", "zkb_test_lde",
@@ -216,14 +216,17 @@ class Context:
         self.check(self.lib.zkb_upload_trace(self.handle, cols, C.c_uint32(w), C.c_uint64(n), C.byref(d)))
         return d.value
 
-    def training_trace_device(self, raw_rows, n, seed):
-        """raw_rows: list of rows of `half` field elements (the distinct raw states).  Returns (device ptr, first row, last row)."""
+    def training_trace_device(self, raw_rows, n, key=None):
+        """raw_rows: list of rows of `half` field elements (the distinct raw states); key: 32 bytes for the ChaCha20 mask stream
+        (tests) or None = OS entropy, like the reference's thread_rng.  Returns (device ptr, first row, last row)."""
+        if key is not None and len(key) != 32:
+            raise ValueError("mask key must be 32 bytes")
         half = len(raw_rows[0])
         rb = b"".join(fe_bytes(x) for row in raw_rows for x in row)
         d = C.c_void_p()
         first, last = C.create_string_buffer(32 * half), C.create_string_buffer(32 * half)
         self.check(self.lib.zkb_training_trace_device(self.handle, rb, C.c_uint32(len(raw_rows)), C.c_uint32(half), C.c_uint64(n),
-                                                      C.c_uint64(seed), C.byref(d), first, last))
+                                                      key, C.byref(d), first, last))
         dec = lambda buf: [fe_int(buf.raw[16 * i:16 * i + 16]) for i in range(2 * half)]
         return d.value, dec(first), dec(last)
 

@@ -180,13 +180,15 @@ class TrainingUpdateProver(Prover):
         data[last:, :flat_len] = _add_mod_rows(states[-1], masks[last:])
         return TraceTable(np.ascontiguousarray(data.transpose(1, 0, 2)))
 
-    def build_trace_device(self, seed=0, ctx=None):
-        """The same trace built on the GPU: only the distinct raw states cross PCIe; the 64-bit masks come from a
-        counter-based generator on the device (the reference draws them from an unseeded thread_rng, src/training/prover.rs:117-121)."""
+    def build_trace_device(self, key=None, ctx=None):
+        """The same trace built on the GPU: only the distinct raw states cross PCIe; the 64-bit blinding masks are a
+        ChaCha20 keystream generated on the device.  key=None (the default) keys it from OS entropy — the reference draws its
+        masks from rand::thread_rng(), an OS-seeded CSPRNG (src/training/prover.rs:117-121), and the masks are all that hides the
+        raw model state behind the public boundary rows.  Pass 32 key bytes only for reproducible tests."""
         from .trace import DeviceTrace
         ctx = ctx or self.context()
         states = self.raw_states()
-        ptr, first, last = ctx.training_trace_device(states, self.trace_length, seed)
+        ptr, first, last = ctx.training_trace_device(states, self.trace_length, key)
         return DeviceTrace(ctx, ptr, 2 * len(states[0]), self.trace_length, first, last)
 
     def get_pub_inputs(self, trace):
