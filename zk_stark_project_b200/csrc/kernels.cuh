@@ -14,6 +14,7 @@
 #pragma once
 #include "f128.cuh"
 #include "blake3.cuh"
+#include "coin.cuh"
 
 namespace zkb {
 
@@ -382,12 +383,13 @@ struct EvalParams {
     uint32_t n_groups;
     uint32_t g_off[ZKB_MAX_GROUPS + 1];  // assertion ranges per boundary group
     fe g_point[ZKB_MAX_GROUPS];   // g^step of the group's divisor (x - g^step)
-    const uint32_t* a_col;        // per assertion: column, value, coefficient
-    const fe* a_val;
+    const uint32_t* a_col;        // per assertion of this column window: column, index into the global (sorted) assertion list
+    const uint32_t* a_sel;
+    const fe* a_val;              // global assertion values / coefficients (device-resident: written per proof, read by index)
     const fe* a_coef;
     const fe* zinv;               // 1/(x^n - 1) for the 2^log_ce cosets used
     fe g_last;                    // g^(n-1): transition exemption point
-    fe k;                         // aggregation scaling factor (src/aggregation/air.rs:108)
+    const fe* params;             // aggregation: params[0] = scaling factor k (src/aggregation/air.rs:108)
     const fe* periodic;           // MiMC: round-constant column over the ce domain, length per_len
     uint32_t per_mask;
     PowTab roots; uint32_t log_tab;
@@ -400,16 +402,24 @@ struct EvalParams {
 
 // B_g coefficients: bc[m][g] = sum_{a in group g} coef_a * polys[m][col_a]  (minus sum_a coef_a * value_a at m = 0);
 // one warp per coefficient row, lanes stride over the group's assertions
-struct BoundaryGroups { uint32_t n_groups; uint32_t g_off[ZKB_MAX_GROUPS + 1]; fe g_const[ZKB_MAX_GROUPS]; };
+struct BoundaryGroups { uint32_t n_groups; uint32_t g_off[ZKB_MAX_GROUPS + 1]; };
 __global__ void __launch_bounds__(256) k_boundary_combine(const fe* __restrict__ polys, uint32_t n, uint32_t w, const uint32_t* __restrict__ a_col,
-                                                          const fe* __restrict__ a_coef, const BoundaryGroups bg, fe* __restrict__ bc) {
+                                                          const uint32_t* __restrict__ a_sel, const fe* __restrict__ a_coef, const fe* __restrict__ a_val,
+                                                          const BoundaryGroups bg, fe* __restrict__ bc) {
     const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (row >= n) return;
     const fe* pr = polys + (size_t)row * w;
     for (uint32_t g = 0; g < bg.n_groups; g++) {
         acc288 acc; acc288_zero(acc);
-        for (uint32_t a = bg.g_off[g] + lane; a < bg.g_off[g + 1]; a += 32) acc288_mad(acc, fe_load(pr + __ldg(a_col + a)), fe_ldg(a_coef + a));
+        acc288 cst; acc288_zero(cst);   // row 0 only: sum_a coef_a * value_a
+        for (uint32_t a = bg.g_off[g] + lane; a < bg.g_off[g + 1]; a += 32) {
+            const uint32_t ai = __ldg(a_sel + a);
+            const fe cf = fe_ldg(a_coef + ai);
+            acc288_mad(acc, fe_load(pr + __ldg(a_col + a)), cf);
+            if (row == 0) acc288_mad(cst, fe_ldg(a_val + ai), cf);
+        }
         fe s = acc288_reduce(acc);
+        if (row == 0) s = fe_sub(s, acc288_reduce(cst));
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             fe o;
@@ -417,10 +427,7 @@ __global__ void __launch_bounds__(256) k_boundary_combine(const fe* __restrict__
             o.x[2] = __shfl_down_sync(0xffffffffu, s.x[2], off); o.x[3] = __shfl_down_sync(0xffffffffu, s.x[3], off);
             s = fe_add(s, o);
         }
-        if (lane == 0) {
-            if (row == 0) s = fe_sub(s, bg.g_const[g]);
-            fe_store(bc + (size_t)row * bg.n_groups + g, s);
-        }
+        if (lane == 0) fe_store(bc + (size_t)row * bg.n_groups + g, s);
     }
 }
 
@@ -466,9 +473,10 @@ __global__ void __launch_bounds__(128) k_eval_constraints(const EvalParams p) {
         acc288 tacc; acc288_zero(tacc);
         if (p.air_id == ZKB_AIR_AGGREGATION) {
             const uint32_t d = p.n_trans;
+            const fe kf = fe_ldg(p.params);
             for (uint32_t c = 0; c < d; c++) {
                 fe dn = fe_sub(fe_load(nxt + c * cs), fe_load(cur + c * cs));
-                fe ev = fe_sub(fe_mul(p.k, dn), fe_load(nxt + (size_t)(c + d) * cs));
+                fe ev = fe_sub(fe_mul(kf, dn), fe_load(nxt + (size_t)(c + d) * cs));
                 acc288_mad(tacc, fe_ldg(p.tcoef + c), ev);
             }
         } else if (p.air_id == ZKB_AIR_MIMC) {
@@ -492,8 +500,9 @@ __global__ void __launch_bounds__(128) k_eval_constraints(const EvalParams p) {
             } else {
                 acc288 bacc; acc288_zero(bacc);
                 for (uint32_t a = p.g_off[g]; a < p.g_off[g + 1]; a++) {
-                    fe v = fe_sub(fe_load(cur + (size_t)__ldg(p.a_col + a) * cs), fe_ldg(p.a_val + a));
-                    acc288_mad(bacc, fe_ldg(p.a_coef + a), v);
+                    const uint32_t ai = __ldg(p.a_sel + a);
+                    fe v = fe_sub(fe_load(cur + (size_t)__ldg(p.a_col + a) * cs), fe_ldg(p.a_val + ai));
+                    acc288_mad(bacc, fe_ldg(p.a_coef + ai), v);
                 }
                 sum = acc288_reduce(bacc);
             }
@@ -522,8 +531,8 @@ __global__ void __launch_bounds__(128) k_eval_constraints(const EvalParams p) {
 // polys row-major [n][w]; block c handles rows [c*R, (c+1)*R), thread j handles column j.
 // A block of 256 threads = nsub row-chunks x wq columns (wq = power of two >= w); chunk q covers rows [q*R, (q+1)*R).
 __global__ void __launch_bounds__(256) k_ood_partial(const fe* __restrict__ polys, uint32_t n, uint32_t w, uint32_t R, uint32_t log_wq,
-                                                      fe z, fe zg, fe zR, fe zgR,
-                                                      fe* __restrict__ part_z, fe* __restrict__ part_zg) {
+                                                      const DevTs* __restrict__ ts, fe* __restrict__ part_z, fe* __restrict__ part_zg) {
+    const fe z = ts->z, zg = ts->zg, zR = ts->zR, zgR = ts->zgR;   // R must be 64 (k_fs_constraint_root)
     // z^(R c), (zg)^(R c) of each row chunk in the block: one thread per chunk raises z^R to the chunk index (<= 2 log2(n/R)
     // multiplications, against 2 R wq for the chunk itself) instead of the host tabulating n/R powers per proof
     // The chunk itself is a dot product with z^0..z^(R-1) (tabulated once per block, R <= 64) accumulated as exact 288-bit
@@ -582,8 +591,9 @@ __global__ void __launch_bounds__(1024) k_col_sum(const fe* __restrict__ part, u
     if (gy == 0 && j < w) fe_store(out + j, s);
 }
 // CompositionPoly::evaluate_at: H_i(z) for contiguous coefficient columns [c][n]; one block per column chunk
-__global__ void __launch_bounds__(256) k_poly_eval_partial(const fe* __restrict__ coef, uint32_t n, uint32_t Q, fe z, fe zQ,
+__global__ void __launch_bounds__(256) k_poly_eval_partial(const fe* __restrict__ coef, uint32_t n, uint32_t Q, const DevTs* __restrict__ ts,
                                                            fe* __restrict__ part) {
+    const fe z = ts->z, zQ = ts->zR;   // Q must be 64
     // block handles column blockIdx.y; thread t handles coefficients [t*Q, (t+1)*Q); partial = Horner * z^(t*Q)
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t nt = (n + Q - 1) / Q;
@@ -626,8 +636,9 @@ __global__ void __launch_bounds__(256) k_deep_combine(const fe* __restrict__ pol
 // k_deep_eval: each thread handles RPT rows (one Montgomery batch inversion per thread)
 #define ZKB_DEEP_RPT 8
 // compact = 1 (coset-sharded AB matrix): out index = i * (stored cosets) + local coset, else the natural position i*beta + k
-__global__ void __launch_bounds__(128) k_deep_eval(const LdeMat m, fe z, fe zg, fe az, fe abz, fe azg, PowTab roots, uint32_t log_tab,
+__global__ void __launch_bounds__(128) k_deep_eval(const LdeMat m, const DevTs* __restrict__ ts, PowTab roots, uint32_t log_tab,
                                                    fe* __restrict__ out, uint32_t compact) {
+    const fe z = ts->z, zg = ts->zg, az = ts->az, abz = ts->abz, azg = ts->azg;
     const uint32_t log_N = m.log_n + m.log_beta;
     const uint64_t N = (uint64_t)1 << (m.log_n + m.log_kc);   // rows stored
     const uint64_t nthreads = N / ZKB_DEEP_RPT;
@@ -673,7 +684,8 @@ __global__ void __launch_bounds__(128) k_deep_eval(const LdeMat m, fe z, fe zg, 
 struct FriFoldParams {
     const fe* in; fe* out;
     uint32_t log_m;            // current domain size M = 2^log_m
-    fe alpha, inv3, inv16;
+    const fe* alpha;           // the layer's folding challenge (device transcript)
+    fe inv3, inv16;
     fe w16inv[8];              // w_16^{-k}, k = 0..7
     PowTab roots; uint32_t log_tab;
 };
@@ -704,7 +716,7 @@ __global__ void __launch_bounds__(128) k_fri_fold16(const FriFoldParams p) {
     // p(alpha) = (1/16) sum_k c_k (alpha / x_i)^k,  1/x_i = (1/3) w_M^{-i}
     const uint32_t tab_mask = (1u << p.log_tab) - 1u;
     const uint32_t e = (0u - ((uint32_t)i << (p.log_tab - p.log_m))) & tab_mask;
-    const fe t = fe_mul(fe_mul(p.alpha, p.inv3), powtab(p.roots, e));
+    const fe t = fe_mul(fe_mul(fe_ldg(p.alpha), p.inv3), powtab(p.roots, e));
     fe acc = v[15];
 #pragma unroll
     for (int kq = 14; kq >= 0; kq--) acc = fe_add(fe_mul(acc, t), v[kq]);
@@ -744,11 +756,12 @@ __global__ void k_gather_lde_rows(const LdeMat m, const uint32_t* __restrict__ p
     fe_store(out + idx, fe_load(m.data + lde_addr(m, k, i, j)));
 }
 // FriProver::build_proof / query_layer: rows [e[p + j*rows]]_{j<16}
+// (positions are reduced into the layer's row range: folding a position is p mod rows, rows a power of two)
 __global__ void k_gather_fri_rows(const fe* __restrict__ e, uint64_t rows, const uint32_t* __restrict__ pos, uint32_t npos, fe* __restrict__ out) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= npos * 16) return;
     const uint32_t q = idx >> 4, j = idx & 15;
-    fe_store(out + idx, fe_load(e + __ldg(pos + q) + (uint64_t)j * rows));
+    fe_store(out + idx, fe_load(e + (__ldg(pos + q) & (uint32_t)(rows - 1)) + (uint64_t)j * rows));
 }
 // Merkle authentication nodes: out[i] = digests[idx[i]]
 __global__ void k_gather_digests(const uint32_t* __restrict__ digests, const uint64_t* __restrict__ idx, uint32_t count, uint32_t* __restrict__ out) {

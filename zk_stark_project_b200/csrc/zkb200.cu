@@ -119,6 +119,21 @@ struct zkb_ctx {
     uint32_t log_g = 0;
     bool mg_active = false;             // the proof in flight is sharded
     DevBuf d_bnd_coef, d_bnd_lde;       // boundary numerators as polynomials (constraints_eval_window)
+
+    // ---- device-resident Fiat-Shamir transcript (csrc/coin.cuh) and the openings gathered for the final download -------
+    // d_fs = [DevTs][OOD frame 2w+c][remainder][per commitment: queried rows, full authentication paths] | device-only:
+    // [coefficient powers nt+na][DEEP gammas w+c][scratch 2w].  The first `host_bytes` travel to the host in ONE copy at the
+    // end of a proof; nothing else crosses PCIe after the trace went up.
+    struct FsTree { size_t o_rows, o_paths; uint32_t width, depth; };
+    struct FsLayout { size_t o_ood = 0, o_rem = 0, host_bytes = 0, o_coef = 0, o_gamma = 0, o_scr = 0, total = 0; uint32_t rem_cap = 0; std::vector<FsTree> trees; } fs;
+    DevBuf d_fs, d_in, d_rem_coef;      // d_in: per-proof inputs [assertion values na][AIR params]
+    uint8_t* h_out = nullptr;           // pinned landing area of the final download
+    size_t h_out_cap = 0;
+    cudaEvent_t ev_done = nullptr;      // blocking-sync event: the host thread sleeps instead of spinning while the device works
+    DevTs* dts() const { return d_fs.as<DevTs>(); }
+    fe* fs_fe(size_t off) const { return reinterpret_cast<fe*>(d_fs.as<uint8_t>() + off); }
+    const fe* d_aval() const { return d_in.as<fe>(); }
+    const fe* d_params() const { return d_in.as<fe>() + air.assertions.size(); }
     DevBuf d_lde_rows, d_mg_a, d_mg_b;  // recv view of the LDE; all-gather staging
     std::vector<Digest32> mg_cap;       // heap of the replicated top log G levels: cap[1] = root, cap[G + q] = subtree root q
 
@@ -165,6 +180,7 @@ struct zkb_ctx {
         h_stage_cap = (size_t)8 << 20;
         CK(cudaHostAlloc((void**)&h_stage, h_stage_cap, cudaHostAllocDefault));
         for (auto& x : ev_group) CK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_done, cudaEventBlockingSync | cudaEventDisableTiming));
         CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
         {   // highest priority: the exchange's few blocks must get SM slots as soon as LDE blocks retire
             int lo = 0, hi = 0;
@@ -179,7 +195,7 @@ struct zkb_ctx {
         cudaStreamSynchronize(stream);
         for (DevBuf* b : {&d_trace, &d_bufA, &d_bufB, &d_tmp1, &d_tmp2, &d_lde, &d_tree, &d_small, &d_comp_evals, &d_comp_lde, &d_comp_tree,
                           &d_ab, &d_ab_lde, &d_deep, &d_roots_lo, &d_roots_hi, &d_inv3_lo, &d_inv3_hi, &d_pow3, &d_aux, &d_gather, &d_user_trace, &d_flags,
-                          &d_lde_rows, &d_mg_a, &d_mg_b, &d_bnd_coef, &d_bnd_lde})
+                          &d_lde_rows, &d_mg_a, &d_mg_b, &d_bnd_coef, &d_bnd_lde, &d_fs, &d_in, &d_rem_coef})
             b->release();
         if (comm) { g_nccl.CommDestroy(comm); comm = nullptr; }
         for (auto& b : d_fri_evals) b.release();
@@ -187,6 +203,8 @@ struct zkb_ctx {
         for (auto& kv : tw_cache) kv.second.release();
         if (ev_ok) { for (auto& pr : tev) for (auto& x : pr) cudaEventDestroy(x); for (auto& x : ev_group) cudaEventDestroy(x); cudaStreamDestroy(copy_stream); cudaStreamDestroy(xchg_stream); }
         if (h_stage) cudaFreeHost(h_stage);
+        if (h_out) cudaFreeHost(h_out);
+        if (ev_done) cudaEventDestroy(ev_done);
         if (owns_stream && stream) { cudaStreamDestroy(stream); stream = nullptr; }
     }
 
@@ -414,6 +432,48 @@ struct zkb_ctx {
         fri_layer = 0; fri_committed = false;
         positions.clear();
         mg_active = false;
+        {   // device transcript + openings layout (everything is determined by the shape)
+            auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+            const uint32_t w = air.w, q = air.num_queries;
+            const uint64_t m_last = air.lde_size() >> (4 * fri_layers);
+            fs = FsLayout();
+            fs.o_ood = al(sizeof(DevTs));
+            fs.o_rem = fs.o_ood + (2 * (size_t)w + c) * 16;
+            fs.rem_cap = (uint32_t)std::max<uint64_t>(1, m_last / air.blowup);
+            size_t off = al(fs.o_rem + (size_t)fs.rem_cap * 16);
+            auto add_tree = [&](uint32_t width, uint32_t depth) {
+                FsTree t{off, off + (size_t)q * width * 16, width, depth};
+                off = al(t.o_paths + (size_t)q * depth * 32);
+                fs.trees.push_back(t);
+            };
+            add_tree(w, log_N);
+            add_tree(c, log_N);
+            for (uint32_t l = 0; l < fri_layers; l++) add_tree(16, log2u(fri_domain(l) / 16));
+            fs.host_bytes = off;
+            fs.o_coef = off; off += ((size_t)air.num_transition() + air.assertions.size()) * 16;
+            fs.o_gamma = off; off += ((size_t)w + c) * 16;
+            fs.o_scr = off; off += 2 * (size_t)w * 16;
+            fs.total = off;
+            d_fs.ensure(fs.total);
+            if (h_out_cap < fs.host_bytes) {
+                if (h_out) { cudaFreeHost(h_out); h_out = nullptr; h_out_cap = 0; }
+                CK(cudaHostAlloc((void**)&h_out, fs.host_bytes, cudaHostAllocDefault));
+                h_out_cap = fs.host_bytes;
+            }
+            // transcript: coin seed = hash(Context ++ public inputs), computed here because the host holds the AIR; all else zero
+            DevTs h0;
+            memset(&h0, 0, sizeof(h0));
+            memcpy(h0.seed, coin.seed, 32);
+            h0.nonce = ~0ull;
+            h2d_small(d_fs.p, &h0, sizeof(h0));
+            // per-proof inputs: assertion values (sorted order) and AIR parameters
+            const size_t na = air.assertions.size(), np = air.params.size();
+            std::vector<HF> in(na + np);
+            for (size_t i = 0; i < na; i++) in[i] = air.assertions[i].value;
+            for (size_t i = 0; i < np; i++) in[na + i] = air.params[i];
+            d_in.ensure((na + np + 1) * 16);
+            h2d_small(d_in.p, in.data(), in.size() * 16);
+        }
         stage = ST_BEGUN;
     }
 
@@ -425,6 +485,15 @@ struct zkb_ctx {
     // 16, 32, 48, 48, ... columns: the first copy, which nothing can hide, is short (16 columns), later groups are wide enough
     // that every launch still fills > 25 waves of resident blocks.
     void trace_commit(const uint8_t* const* host_cols, const fe* d_src, uint8_t root_out[32]) {
+        trace_commit_dev(host_cols, d_src);
+        Digest32 root;
+        d2h(root.b, d_tree.as<uint32_t>() + 8, 32);
+        parts.commitments.push_back(root);
+        memcpy(ts.trace_root, root.b, 32);
+        if (root_out) memcpy(root_out, root.b, 32);
+    }
+    // leaves the root at d_tree + 8 words
+    void trace_commit_dev(const uint8_t* const* host_cols, const fe* d_src) {
         if (stage != ST_BEGUN) throw StateError("zkb_trace_commit: call zkb_begin first");
         const uint64_t n = air.n, N = air.lde_size();
         const uint32_t w = air.w;
@@ -483,11 +552,6 @@ struct zkb_ctx {
         t_begin(TS_MERKLE);
         build_merkle(d_tree.as<uint32_t>(), N);
         t_end(TS_MERKLE);
-        Digest32 root;
-        d2h(root.b, d_tree.as<uint32_t>() + 8, 32);
-        parts.commitments.push_back(root);
-        memcpy(ts.trace_root, root.b, 32);
-        if (root_out) memcpy(root_out, root.b, 32);
         // interpolation and LDE are interleaved per group: they are reported together under `lde`
         stage = ST_TRACE;
     }
@@ -648,30 +712,47 @@ struct zkb_ctx {
         paths = batch_proof_bytes(log_N, plan, dig.data());
     }
 
+    // ---- Fiat-Shamir steps.  `digest` = device address of the commitment the coin is reseeded with (one-shot proofs: the whole
+    // channel runs on the device, csrc/coin.cuh); nullptr = the staged API handed us the challenge, which is uploaded instead.
+    void fs_upload(fe* dst, const HF& v) { h2d_small(dst, &v, 16); }
+    void fs_after_trace_root(const uint32_t* digest, const HF* alpha) {
+        if (!digest) fs_upload(&dts()->alpha, *alpha);
+        k_fs_trace_root<<<1, ZKB_FS_THREADS, 0, stream>>>(dts(), digest, air.num_transition() + (uint32_t)air.assertions.size(), fs_fe(fs.o_coef));
+        check_launch();
+    }
+    void fs_after_constraint_root(const uint32_t* digest, const HF* zz) {
+        if (!digest) fs_upload(&dts()->z, *zz);
+        k_fs_constraint_root<<<1, 32, 0, stream>>>(dts(), digest, d_flags.as<uint32_t>(), to_fe(HF::root_of_unity(log_n)));
+        check_launch();
+    }
+    void fs_after_ood(bool with_coin, const HF* deep_alpha) {
+        if (!with_coin) fs_upload(&dts()->deep_alpha, *deep_alpha);
+        k_fs_ood<<<1, ZKB_FS_THREADS, 0, stream>>>(dts(), fs_fe(fs.o_ood), air.w, c, fs_fe(fs.o_scr), fs_fe(fs.o_gamma), with_coin ? 1u : 0u);
+        check_launch();
+    }
+
     // K5.  The evaluator works on a window of `ncols` trace columns starting at global column `col0` (the whole trace on
     // one GPU; this rank's columns in a column-sharded proof).  Every term of the combined evaluation is linear in
     // per-column sums, so per-rank partial results add up to the full composition trace.
-    void constraints_eval_window(const HF& alpha, const LdeMat& mat, uint32_t col0, uint32_t ncols, fe* out) {
+    // The coefficient powers alpha^0.. (transition constraints, then the assertions sorted by (step, column): draw_algebraic,
+    // [A.5]) are in device memory already (k_fs_trace_root); assertion values and AIR parameters are the per-proof inputs d_in.
+    void constraints_eval_window(const LdeMat& mat, uint32_t col0, uint32_t ncols, fe* out) {
         const uint32_t nt = air.num_transition(), na = (uint32_t)air.assertions.size();
         const uint64_t n = air.n, ce = (uint64_t)1 << log_ce;
-        // ConstraintCompositionCoefficients::draw_algebraic: alpha^0.. for transition, continuing for boundary  [A.5]
-        std::vector<HF> tcoef(nt), acoef_all(na);
-        { HF cur = HF::raw(1); for (auto& x : tcoef) { x = cur; cur = cur * alpha; } for (auto& x : acoef_all) { x = cur; cur = cur * alpha; } }
         const bool windowed = !(col0 == 0 && ncols == air.w);
         if (windowed && air.id == ZKB_AIR_ID_AGGREGATION) throw InvalidArg("the aggregation AIR couples columns i and i+d and cannot be column-sharded");
         EvalParams p{};
         p.lde = mat; p.air_id = air.id; p.log_ce = log_ce;
         p.n_trans = windowed ? ncols : nt;
         const HF g = HF::root_of_unity(log_n);
-        std::vector<HF> acoef, aval;
-        std::vector<uint32_t> acol;
+        std::vector<uint32_t> acol, asel;
         uint32_t ng = 0;
         for (uint32_t i = 0; i < na; i++) {
             if (i == 0 || air.assertions[i].step != air.assertions[i - 1].step) {
                 p.g_off[ng] = (uint32_t)acol.size(); p.g_point[ng] = to_fe(g.pow(air.assertions[i].step)); ng++;
             }
             const uint32_t col = air.assertions[i].col;
-            if (col >= col0 && col < col0 + ncols) { acol.push_back(col - col0); aval.push_back(air.assertions[i].value); acoef.push_back(acoef_all[i]); }
+            if (col >= col0 && col < col0 + ncols) { acol.push_back(col - col0); asel.push_back(i); }
         }
         const uint32_t nl = (uint32_t)acol.size();
         p.g_off[ng] = nl; p.n_groups = ng;
@@ -692,22 +773,20 @@ struct zkb_ctx {
         }
         static const std::vector<HF> no_per;
         const std::vector<HF>& per = air.id == ZKB_AIR_ID_MIMC ? per_cache : no_per;
-        // pack the small arrays into one device buffer
-        const uint32_t ntl = p.n_trans;
-        size_t off_t = 0, off_c = off_t + (size_t)ntl * 16, off_v = off_c + (size_t)nl * 16, off_z = off_v + (size_t)nl * 16, off_p = off_z + ce * 16,
-               off_col = off_p + per.size() * 16, total = off_col + (size_t)nl * 4 + 16;
+        // pack the shape-dependent small arrays into one device buffer
+        size_t off_z = 0, off_p = off_z + ce * 16, off_col = off_p + per.size() * 16, off_sel = off_col + (size_t)nl * 4, total = off_sel + (size_t)nl * 4 + 16;
         std::vector<uint8_t> pack(total);
-        memcpy(&pack[off_t], tcoef.data() + (windowed ? col0 : 0), (size_t)ntl * 16);
-        if (nl) { memcpy(&pack[off_c], acoef.data(), (size_t)nl * 16); memcpy(&pack[off_v], aval.data(), (size_t)nl * 16); memcpy(&pack[off_col], acol.data(), (size_t)nl * 4); }
         memcpy(&pack[off_z], zinv.data(), ce * 16); if (!per.empty()) memcpy(&pack[off_p], per.data(), per.size() * 16);
+        if (nl) { memcpy(&pack[off_col], acol.data(), (size_t)nl * 4); memcpy(&pack[off_sel], asel.data(), (size_t)nl * 4); }
         d_aux.ensure(total);
         h2d_small(d_aux.p, pack.data(), total);
         uint8_t* base = d_aux.as<uint8_t>();
-        p.tcoef = (const fe*)(base + off_t); p.a_coef = (const fe*)(base + off_c); p.a_val = (const fe*)(base + off_v);
-        p.zinv = (const fe*)(base + off_z); p.periodic = (const fe*)(base + off_p); p.a_col = (const uint32_t*)(base + off_col);
+        const fe* coef = fs_fe(fs.o_coef);
+        p.tcoef = coef + (windowed ? col0 : 0); p.a_coef = coef + nt; p.a_val = d_aval(); p.params = d_params();
+        p.zinv = (const fe*)(base + off_z); p.periodic = (const fe*)(base + off_p);
+        p.a_col = (const uint32_t*)(base + off_col); p.a_sel = (const uint32_t*)(base + off_sel);
         p.per_mask = per.empty() ? 0 : (uint32_t)per.size() - 1;
         p.g_last = to_fe(g.pow((u128)(n - 1)));
-        p.k = air.id == ZKB_AIR_ID_AGGREGATION ? to_fe(air.params[0]) : fe{};
         p.roots = roots; p.log_tab = log_tab;
         p.out = out;
         // Boundary numerators.  Per-point sums cost nl multiplications at each of the ce*n points; combining the asserted
@@ -723,14 +802,10 @@ struct zkb_ctx {
                 BoundaryGroups bg{};
                 bg.n_groups = ng;
                 for (uint32_t gi = 0; gi <= ng; gi++) bg.g_off[gi] = p.g_off[gi];
-                for (uint32_t gi = 0; gi < ng; gi++) {
-                    HF cst;
-                    for (uint32_t a = p.g_off[gi]; a < p.g_off[gi + 1]; a++) cst = cst + acoef[a] * aval[a];
-                    bg.g_const[gi] = to_fe(cst);
-                }
                 d_bnd_coef.ensure(n * ng * 16);
                 d_bnd_lde.ensure(n * ce * ng * 16);
-                k_boundary_combine<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(d_polys, (uint32_t)n, ncols, p.a_col, p.a_coef, bg, d_bnd_coef.as<fe>());
+                k_boundary_combine<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(d_polys, (uint32_t)n, ncols, p.a_col, p.a_sel, p.a_coef, p.a_val, bg,
+                                                                                        d_bnd_coef.as<fe>());
                 check_launch();
                 Xform xb{d_bnd_coef.as<fe>(), ng, 0, d_bnd_lde.as<fe>(), ng, 0, ng, log_n, false, true, log_n + log_ce, false, HF()};
                 const uint32_t lp = run_xform(xb, d_tmp1, d_tmp2);
@@ -745,13 +820,14 @@ struct zkb_ctx {
         else k_eval_constraints<1><<<(unsigned)((points + 127) / 128), 128, 0, stream>>>(p);
         check_launch();
     }
-    void constraints_eval(const HF& alpha, uint8_t* evals_out) {
+    // the coefficient powers must be in place (fs_after_trace_root)
+    void constraints_eval_dev() {
         if (stage != ST_TRACE) throw StateError("zkb_constraints_eval: trace is not committed");
         t_begin(TS_CONSTR);
         const uint64_t n = air.n, ce = (uint64_t)1 << log_ce;
         d_comp_evals.ensure(n * ce * 16);
         if (!mg_active) {
-            constraints_eval_window(alpha, lde_mat(), 0, air.w, d_comp_evals.as<fe>());
+            constraints_eval_window(lde_mat(), 0, air.w, d_comp_evals.as<fe>());
         } else {
             // column-sharded: partial evaluation over this rank's columns, all-gather, field sum
             // reduce-scatter by hand (NCCL cannot add mod p): slice q of every rank's partial vector goes to rank q, which
@@ -760,7 +836,7 @@ struct zkb_ctx {
             const uint64_t total = n * ce, sl = total / G;
             d_mg_a.ensure(total * 16);
             d_mg_b.ensure(total * 16 + sl * 16);
-            constraints_eval_window(alpha, lde_mat(), mg_rank * wl, wl, d_mg_a.as<fe>());
+            constraints_eval_window(lde_mat(), mg_rank * wl, wl, d_mg_a.as<fe>());
             NK(g_nccl.GroupStart());
             for (uint32_t q = 0; q < G; q++) {
                 NK(g_nccl.Send(d_mg_a.as<fe>() + q * sl, sl * 16, ncclUint8, (int)q, comm, stream));
@@ -773,12 +849,17 @@ struct zkb_ctx {
             NK(g_nccl.AllGather(mine, d_comp_evals.p, sl * 16, ncclUint8, comm, stream));
         }
         t_end(TS_CONSTR);
-        if (evals_out) d2h(evals_out, d_comp_evals.p, n * ce * 16);
         stage = ST_EVAL;
     }
+    void constraints_eval(const HF& alpha, uint8_t* evals_out) {
+        if (stage != ST_TRACE) throw StateError("zkb_constraints_eval: trace is not committed");
+        fs_after_trace_root(nullptr, &alpha);
+        constraints_eval_dev();
+        if (evals_out) d2h(evals_out, d_comp_evals.p, (air.n << log_ce) * 16);
+    }
 
-    // K6
-    void constraints_commit(uint8_t root_out[32]) {
+    // K6.  Leaves the root at d_comp_tree + 8 words and the degree flag in d_flags.
+    void constraints_commit_dev() {
         if (stage != ST_EVAL) throw StateError("zkb_constraints_commit: constraints are not evaluated");
         t_begin(TS_COMP);
         const uint64_t n = air.n, N = air.lde_size(), cen = n << log_ce;
@@ -824,6 +905,10 @@ struct zkb_ctx {
         }
         build_merkle(d_comp_tree.as<uint32_t>(), N);
         t_end(TS_COMP);
+        stage = ST_COMP;
+    }
+    void constraints_commit(uint8_t root_out[32]) {
+        constraints_commit_dev();
         Digest32 root;
         uint32_t bad_degree = 0;
         CK(cudaMemcpyAsync(&bad_degree, d_flags.p, 4, cudaMemcpyDeviceToHost, stream));
@@ -833,28 +918,30 @@ struct zkb_ctx {
         parts.commitments.push_back(root);
         memcpy(ts.constraint_root, root.b, 32);
         if (root_out) memcpy(root_out, root.b, 32);
-        stage = ST_COMP;
     }
 
     // K7.  Trace polynomials are held per rank for its own columns (all of them on one GPU); a column-sharded proof
-    // all-gathers the 2*w_local evaluations.
-    void ood_eval(const HF& z_) {
+    // all-gathers the 2*w_local evaluations.  z and its powers are read from the device transcript (k_fs_constraint_root);
+    // the frame lands in d_fs: [T_j(z) w][T_j(zg) w][H_i(z) c].
+    void ood_eval_dev() {
         if (stage != ST_COMP) throw StateError("zkb_ood_eval: constraint commitment is missing");
         t_begin(TS_OOD);
-        z = z_; zg = z * HF::root_of_unity(log_n);
         const uint64_t n = air.n; const uint32_t w = air.w;
         const uint32_t wl = mg_active ? (w / (uint32_t)mg_world) : w;   // columns of d_polys
-        const uint32_t R = 64;
+        const uint32_t R = 64;                                          // k_fs_constraint_root tabulates z^64
         const uint32_t nch = (uint32_t)((n + R - 1) / R);
         uint32_t log_wq = 0; while ((1u << log_wq) < wl) log_wq++;
         const uint32_t nsub = 256u >> log_wq;
-        // layout of d_small: [part_z nch*wl][part_zg nch*wl][hpart nt*c][ood 2wl][ood_h c][gathered 2w]
+        // layout of d_small: [part_z nch*wl][part_zg nch*wl][hpart nt*c][local frame 2wl][gathered 2w][scratch]
         const uint32_t Q = 64;
         const uint32_t nt = (uint32_t)((n + Q - 1) / Q);
-        size_t o_pz = 0, o_pzg = o_pz + (size_t)nch * wl, o_hp = o_pzg + (size_t)nch * wl, o_ood = o_hp + (size_t)c * nt,
-               o_ga = o_ood + 2 * (size_t)wl + c, o_sc = o_ga + 2 * (size_t)w, total = o_sc + 64 * 256;
+        size_t o_pz = 0, o_pzg = o_pz + (size_t)nch * wl, o_hp = o_pzg + (size_t)nch * wl, o_loc = o_hp + (size_t)c * nt,
+               o_ga = o_loc + 2 * (size_t)wl, o_sc = o_ga + 2 * (size_t)w, total = o_sc + 64 * 256;
         d_small.ensure(total * 16);
         fe* sm = d_small.as<fe>();
+        fe* frame = fs_fe(fs.o_ood);
+        fe* cur_out = mg_active ? sm + o_loc : frame;
+        fe* nxt_out = mg_active ? sm + o_loc + wl : frame + w;
         // column sums of a [chunks][cols] matrix; many chunks are first folded 64-fold by treating the matrix as
         // [chunks/64][64*cols], so the reduction is spread over 2*cols blocks instead of cols/32
         auto col_sum = [&](const fe* part, uint32_t chunks, uint32_t cols, fe* out) {
@@ -866,67 +953,68 @@ struct zkb_ctx {
             k_col_sum<<<(cols + 31) / 32, dim3(32, 32), 0, stream>>>(part, chunks, cols, out);
             check_launch();
         };
-        k_ood_partial<<<(nch + nsub - 1) / nsub, 256, 0, stream>>>(d_polys, (uint32_t)n, wl, R, log_wq, to_fe(z), to_fe(zg), to_fe(z.pow(R)), to_fe(zg.pow(R)),
-                                                                   sm + o_pz, sm + o_pzg);
+        k_ood_partial<<<(nch + nsub - 1) / nsub, 256, 0, stream>>>(d_polys, (uint32_t)n, wl, R, log_wq, dts(), sm + o_pz, sm + o_pzg);
         check_launch();
-        col_sum(sm + o_pz, nch, wl, sm + o_ood);
-        col_sum(sm + o_pzg, nch, wl, sm + o_ood + wl);
+        col_sum(sm + o_pz, nch, wl, cur_out);
+        col_sum(sm + o_pzg, nch, wl, nxt_out);
         // H_i(z) from the composition column coefficients (still in d_bufA; replicated on every rank)
         {
             dim3 grid((nt + 255) / 256, c);
-            k_poly_eval_partial<<<grid, 256, 0, stream>>>(d_bufA.as<fe>(), (uint32_t)n, Q, to_fe(z), to_fe(z.pow(Q)), sm + o_hp);
+            k_poly_eval_partial<<<grid, 256, 0, stream>>>(d_bufA.as<fe>(), (uint32_t)n, Q, dts(), sm + o_hp);
             check_launch();
-            col_sum(sm + o_hp, nt, c, sm + o_ood + 2 * (size_t)wl);
+            col_sum(sm + o_hp, nt, c, frame + 2 * (size_t)w);
         }
-        std::vector<HF> host(2 * (size_t)wl + c);
-        d2h(host.data(), sm + o_ood, host.size() * 16);  // the frame and the H values are adjacent
-        ood_cur.assign(w, HF()); ood_next.assign(w, HF());
-        if (!mg_active) {
-            for (uint32_t j = 0; j < w; j++) { ood_cur[j] = host[j]; ood_next[j] = host[w + j]; }
-        } else {
-            NK(g_nccl.AllGather(sm + o_ood, sm + o_ga, 2 * (size_t)wl * 16, ncclUint8, comm, stream));
-            std::vector<HF> all(2 * (size_t)w);
+        if (mg_active) {
+            // per-rank [cur wl][next wl] blocks -> the global frame, put back on the device for k_fs_ood
+            NK(g_nccl.AllGather(sm + o_loc, sm + o_ga, 2 * (size_t)wl * 16, ncclUint8, comm, stream));
+            std::vector<HF> all(2 * (size_t)w), glob(2 * (size_t)w);
             d2h(all.data(), sm + o_ga, all.size() * 16);
             for (int r = 0; r < mg_world; r++)
-                for (uint32_t jl = 0; jl < wl; jl++) { ood_cur[r * wl + jl] = all[(size_t)r * 2 * wl + jl]; ood_next[r * wl + jl] = all[(size_t)r * 2 * wl + wl + jl]; }
+                for (uint32_t jl = 0; jl < wl; jl++) { glob[r * wl + jl] = all[(size_t)r * 2 * wl + jl]; glob[w + r * wl + jl] = all[(size_t)r * 2 * wl + wl + jl]; }
+            h2d_small(frame, glob.data(), glob.size() * 16);
         }
-        ood_h.assign(c, HF());
-        for (uint32_t i = 0; i < c; i++) ood_h[i] = host[2 * (size_t)wl + i];
         t_end(TS_OOD);
         stage = ST_OOD;
     }
+    void ood_fetch() {   // host copy of the frame (staged API, sharded proofs)
+        const uint32_t w = air.w;
+        std::vector<HF> host(2 * (size_t)w + c);
+        d2h(host.data(), fs_fe(fs.o_ood), host.size() * 16);
+        ood_cur.assign(host.begin(), host.begin() + w);
+        ood_next.assign(host.begin() + w, host.begin() + 2 * (size_t)w);
+        ood_h.assign(host.begin() + 2 * (size_t)w, host.end());
+    }
+    void ood_eval(const HF& z_) {
+        if (stage != ST_COMP) throw StateError("zkb_ood_eval: constraint commitment is missing");
+        z = z_; zg = z * HF::root_of_unity(log_n);
+        fs_after_constraint_root(nullptr, &z_);
+        ood_eval_dev();
+        ood_fetch();
+    }
 
-    // K8
-    void deep_compose(const HF& alpha) {
+    // K8.  The DEEP coefficients gamma^0.. (trace columns, then composition columns: draw_algebraic [A.5]) and the constants
+    // A(z), (A+B)(z), A(zg) are in device memory (k_fs_ood).
+    void deep_compose_dev() {
         if (stage != ST_OOD) throw StateError("zkb_deep_compose: OOD frame is missing");
         t_begin(TS_DEEP);
-        deep_alpha = alpha;
         const uint64_t n = air.n, N = air.lde_size(); const uint32_t w = air.w;
-        // DeepCompositionCoefficients::draw_algebraic: alpha^0.. for trace columns, continuing for H columns  [A.5]
-        std::vector<HF> g(w + c);
-        { HF cur = HF::raw(1); for (auto& x : g) { x = cur; cur = cur * alpha; } }
-        HF az, azg, bz;
-        for (uint32_t j = 0; j < w; j++) { az = az + g[j] * ood_cur[j]; azg = azg + g[j] * ood_next[j]; }
-        for (uint32_t i = 0; i < c; i++) bz = bz + g[w + i] * ood_h[i];
-        d_aux.ensure((w + c) * 16);
-        h2d_small(d_aux.p, g.data(), g.size() * 16);
+        const fe* gamma = fs_fe(fs.o_gamma);
         d_ab.ensure(n * 2 * 16);
         if (!mg_active) {
-            k_deep_combine<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(d_polys, (uint32_t)n, w, d_aux.as<fe>(), d_bufA.as<fe>(), c,
-                                                                              d_aux.as<fe>() + w, d_ab.as<fe>());
+            k_deep_combine<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(d_polys, (uint32_t)n, w, gamma, d_bufA.as<fe>(), c, gamma + w, d_ab.as<fe>());
             check_launch();
         } else {
             // partial A over this rank's columns -> all-gather -> field sum -> add the (replicated) H part
             const uint32_t wl = w / (uint32_t)mg_world;
             d_mg_a.ensure(n * 2 * 16);
             d_mg_b.ensure(n * 2 * 16 * mg_world);
-            k_deep_combine<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(d_polys, (uint32_t)n, wl, d_aux.as<fe>() + (size_t)mg_rank * wl,
-                                                                              d_bufA.as<fe>(), 0, d_aux.as<fe>() + w, d_mg_a.as<fe>());
+            k_deep_combine<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(d_polys, (uint32_t)n, wl, gamma + (size_t)mg_rank * wl, d_bufA.as<fe>(), 0,
+                                                                              gamma + w, d_mg_a.as<fe>());
             check_launch();
             NK(g_nccl.AllGather(d_mg_a.p, d_mg_b.p, n * 2 * 16, ncclUint8, comm, stream));
             k_sum_partials<<<(unsigned)((2 * n + 255) / 256), 256, 0, stream>>>(d_mg_b.as<fe>(), mg_world, 2 * n, 2 * n, d_ab.as<fe>());
             check_launch();
-            k_deep_add_h<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_ab.as<fe>(), (uint32_t)n, d_bufA.as<fe>(), c, d_aux.as<fe>() + w);
+            k_deep_add_h<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_ab.as<fe>(), (uint32_t)n, d_bufA.as<fe>(), c, gamma + w);
             check_launch();
         }
         d_ab_lde.ensure(N * 2 * 16);
@@ -935,8 +1023,7 @@ struct zkb_ctx {
             Xform x{d_ab.as<fe>(), 2, 0, d_ab_lde.as<fe>(), 2, 0, 2, log_n, false, true, log_N, false, HF()};
             ab_log_p = run_xform(x, d_tmp1, d_tmp2);
             const uint64_t threads = N / ZKB_DEEP_RPT;
-            k_deep_eval<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(ab_mat(), to_fe(z), to_fe(zg), to_fe(az), to_fe(az + bz), to_fe(azg),
-                                                                              roots, log_tab, d_deep.as<fe>(), 0);
+            k_deep_eval<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(ab_mat(), dts(), roots, log_tab, d_deep.as<fe>(), 0);
             check_launch();
         } else {
             // multi-GPU: extend and evaluate on this rank's cosets, all-gather the evaluations, restore natural order
@@ -947,8 +1034,7 @@ struct zkb_ctx {
             ab_log_p = run_xform(x, d_tmp1, d_tmp2);
             d_mg_a.ensure(Nloc * 16); d_mg_b.ensure(N * 16);
             const uint64_t threads = Nloc / ZKB_DEEP_RPT;
-            k_deep_eval<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(ab_mat(), to_fe(z), to_fe(zg), to_fe(az), to_fe(az + bz), to_fe(azg),
-                                                                              roots, log_tab, d_mg_a.as<fe>(), 1);
+            k_deep_eval<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(ab_mat(), dts(), roots, log_tab, d_mg_a.as<fe>(), 1);
             check_launch();
             NK(g_nccl.AllGather(d_mg_a.p, d_mg_b.p, Nloc * 16, ncclUint8, comm, stream));
             k_permute_coset_items<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(d_mg_b.as<uint32_t>(), d_deep.as<uint32_t>(), log_n, log_beta,
@@ -960,11 +1046,18 @@ struct zkb_ctx {
         fri_layer = 0; fri_committed = false;
         stage = ST_DEEP;
     }
+    void deep_compose(const HF& alpha) {
+        if (stage != ST_OOD) throw StateError("zkb_deep_compose: OOD frame is missing");
+        deep_alpha = alpha;
+        fs_after_ood(false, &alpha);
+        deep_compose_dev();
+    }
 
     // K9
     const fe* fri_cur_evals() const { return fri_layer == 0 ? d_deep.as<fe>() : d_fri_evals[fri_layer].as<fe>(); }
     uint64_t fri_domain(uint32_t layer) const { return air.lde_size() >> (4 * layer); }
-    void fri_commit_layer(uint8_t root_out[32]) {
+    // leaves the layer's root at d_fri_tree[layer] + 8 words
+    void fri_commit_layer_dev() {
         if (stage != ST_DEEP || fri_layer >= fri_layers || fri_committed) throw StateError("zkb_fri_commit_layer: out of order");
         const uint64_t M = fri_domain(fri_layer), rows = M / 16;
         DevBuf& tree = d_fri_tree[fri_layer];
@@ -972,22 +1065,25 @@ struct zkb_ctx {
         k_hash_strided_rows<<<(unsigned)((rows + 127) / 128), 128, 0, stream>>>(fri_cur_evals(), rows, 16, tree.as<uint32_t>() + rows * 8);
         check_launch();
         build_merkle(tree.as<uint32_t>(), rows);
+        fri_committed = true;
+    }
+    void fri_commit_layer(uint8_t root_out[32]) {
+        fri_commit_layer_dev();
         Digest32 root;
-        d2h(root.b, tree.as<uint32_t>() + 8, 32);
+        d2h(root.b, d_fri_tree[fri_layer].as<uint32_t>() + 8, 32);
         parts.commitments.push_back(root);
         memcpy(ts.fri_roots[fri_layer], root.b, 32);
         if (root_out) memcpy(root_out, root.b, 32);
-        fri_committed = true;
     }
-    void fri_fold(const HF& alpha) {
+    // the folding challenge is dts()->fri_alpha[fri_layer]
+    void fri_fold_dev() {
         if (stage != ST_DEEP || !fri_committed) throw StateError("zkb_fri_fold: commit the layer first");
         const uint64_t M = fri_domain(fri_layer), rows = M / 16;
-        alpha.to_bytes(ts.fri_alphas[fri_layer]);
         DevBuf& nxt = d_fri_evals[fri_layer + 1];
         nxt.ensure(rows * 16);
         FriFoldParams p{};
         p.in = fri_cur_evals(); p.out = nxt.as<fe>(); p.log_m = log2u(M);
-        p.alpha = to_fe(alpha); p.inv3 = to_fe(HF::from_u64(3).inv()); p.inv16 = to_fe(HF::from_u64(16).inv());
+        p.alpha = &dts()->fri_alpha[fri_layer]; p.inv3 = to_fe(HF::from_u64(3).inv()); p.inv16 = to_fe(HF::from_u64(16).inv());
         HF wi = HF::root_of_unity(4).inv(), x = HF::raw(1);
         for (int q = 0; q < 8; q++) { p.w16inv[q] = to_fe(x); x = x * wi; }
         p.roots = roots; p.log_tab = log_tab;
@@ -997,21 +1093,41 @@ struct zkb_ctx {
         fri_committed = false;
         ts.n_fri_layers = fri_layer;
     }
-    void fri_remainder(Digest32* commitment) {
+    void fri_fold(const HF& alpha) {
+        if (stage != ST_DEEP || !fri_committed) throw StateError("zkb_fri_fold: commit the layer first");
+        alpha.to_bytes(ts.fri_alphas[fri_layer]);
+        fs_upload(&dts()->fri_alpha[fri_layer], alpha);
+        fri_fold_dev();
+    }
+    // FriProver::set_remainder  [A.10]: interpolate the last layer over 3*<w_M> on the device (the ordinary inverse transform
+    // + the offset scaling of CompositionPoly::new), keep M/beta coefficients reversed, commit them (k_fs_remainder)
+    void fri_remainder_dev(bool with_coin) {
         if (stage != ST_DEEP || fri_layer != fri_layers || fri_committed) throw StateError("zkb_fri_remainder: fold all layers first");
         const uint64_t M = fri_domain(fri_layer);
-        std::vector<HF> ev_(M);
-        d2h(ev_.data(), fri_cur_evals(), M * 16);
-        std::vector<HF> coef = host_interpolate(ev_, HF::from_u64(3));  // set_remainder  [A.10]
-        const uint64_t rs = M / air.blowup;
-        parts.remainder.assign(coef.begin(), coef.begin() + rs);
-        std::reverse(parts.remainder.begin(), parts.remainder.end());
+        const uint32_t rs = (uint32_t)(M / air.blowup);
+        // (rs == 0 — the last layer is shorter than the blowup — yields an empty remainder, which the verifier rejects as it
+        // does Winterfell's: the options do not fit the trace length)
+        if (rs > fs.rem_cap || rs > 1024) throw InvalidArg("unsupported FRI remainder size");
+        d_rem_coef.ensure(M * 16);
+        Xform x{fri_cur_evals(), 1, 0, d_rem_coef.as<fe>(), 1, 0, 1, log2u(M), true, false, 0, false, HF()};
+        run_xform(x, d_tmp1, d_tmp2);
+        d_flags.ensure(256);
+        k_scale_pow<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(d_rem_coef.as<fe>(), M, inv3tab, to_fe(HF::from_u64(M).inv()), M, d_flags.as<uint32_t>() + 8);
+        check_launch();
+        k_fs_remainder<<<1, ZKB_FS_THREADS, 0, stream>>>(dts(), d_rem_coef.as<fe>(), rs, fs_fe(fs.o_rem), with_coin ? 1u : 0u);
+        check_launch();
+        stage = ST_FRI_DONE;
+    }
+    void fri_remainder(Digest32* commitment) {
+        fri_remainder_dev(false);
+        const uint32_t rs = (uint32_t)(fri_domain(fri_layer) / air.blowup);
+        parts.remainder.assign(rs, HF());
+        CK(cudaMemcpyAsync(parts.remainder.data(), fs_fe(fs.o_rem), (size_t)rs * 16, cudaMemcpyDeviceToHost, stream));
         Digest32 d;
-        HostCoin::hash_elems(parts.remainder, d.b);
+        d2h(d.b, dts()->rem_commit, 32);
         parts.commitments.push_back(d);
         memcpy(ts.remainder_commitment, d.b, 32);
         if (commitment) *commitment = d;
-        stage = ST_FRI_DONE;
     }
 
     // K10
@@ -1094,83 +1210,151 @@ struct zkb_ctx {
         paths = batch_proof_bytes(depth, plan, host.data() + (size_t)np * width * 16);
     }
 
-    // All openings of a single-GPU proof in one go: every gather kernel is enqueued into its own region of d_gather and ONE
-    // device-to-host copy (one synchronisation) brings rows and authentication nodes back, instead of one round trip per
-    // commitment (trace, composition, every FRI layer).
-    struct QueryReq { uint32_t which; const std::vector<uint32_t>* pos; std::vector<uint8_t>* rows; std::vector<uint8_t>* paths; };
-    void query_all(const std::vector<QueryReq>& reqs) {
-        struct Job { uint32_t width, depth, np; uint64_t domain; const uint32_t* heap; std::vector<std::vector<uint64_t>> plan; size_t nflat, o_pos, o_idx, o_out; };
-        std::vector<Job> jobs(reqs.size());
-        std::vector<uint8_t> up;      // positions and node indices of all jobs, one upload
-        size_t out_bytes = 0;
-        auto pad16 = [](size_t x) { return (x + 15) / 16 * 16; };
-        for (size_t q = 0; q < reqs.size(); q++) {
-            const QueryReq& r = reqs[q]; Job& j = jobs[q];
-            j.np = (uint32_t)r.pos->size();
-            if (j.np == 0 || j.np > 255) throw InvalidArg("bad number of query positions");
-            if (r.which == 0) { j.width = air.w; j.domain = air.lde_size(); j.heap = d_tree.as<uint32_t>(); }
-            else if (r.which == 1) { j.width = c; j.domain = air.lde_size(); j.heap = d_comp_tree.as<uint32_t>(); }
-            else {
-                const uint32_t l = r.which - 2;
-                if (l >= fri_layers) throw InvalidArg("no such FRI layer");
-                j.width = 16; j.domain = fri_domain(l) / 16; j.heap = d_fri_tree[l].as<uint32_t>();
-            }
-            for (uint32_t p : *r.pos) if (p >= j.domain) throw InvalidArg("query position out of range");
-            j.depth = log2u(j.domain);
-            j.plan = plan_batch_proof(j.depth, *r.pos);
-            std::vector<uint64_t> flat;
-            for (auto& v : j.plan) flat.insert(flat.end(), v.begin(), v.end());
-            j.nflat = flat.size();
-            j.o_pos = up.size(); up.resize(pad16(up.size() + (size_t)j.np * 4)); memcpy(&up[j.o_pos], r.pos->data(), (size_t)j.np * 4);
-            j.o_idx = up.size(); up.resize(pad16(up.size() + j.nflat * 8 + 8)); if (j.nflat) memcpy(&up[j.o_idx], flat.data(), j.nflat * 8);
-            j.o_out = out_bytes; out_bytes += pad16((size_t)j.np * j.width * 16 + j.nflat * 32);
-        }
-        const size_t o_out0 = pad16(up.size());
-        d_gather.ensure(o_out0 + out_bytes + 32);
-        uint8_t* base = d_gather.as<uint8_t>();
-        h2d_small(base, up.data(), up.size());
-        for (size_t q = 0; q < reqs.size(); q++) {
-            const Job& j = jobs[q];
-            const uint32_t which = reqs[q].which, th = j.np * j.width;
-            const uint32_t* dpos = (const uint32_t*)(base + j.o_pos);
-            fe* drows = (fe*)(base + o_out0 + j.o_out);
-            if (which == 0) k_gather_lde_rows<<<(th + 127) / 128, 128, 0, stream>>>(lde_mat(), dpos, j.np, drows);
-            else if (which == 1) k_gather_lde_rows<<<(th + 127) / 128, 128, 0, stream>>>(comp_mat(), dpos, j.np, drows);
-            else {
-                const uint32_t l = which - 2;
-                const fe* e = l == 0 ? d_deep.as<fe>() : d_fri_evals[l].as<fe>();
-                k_gather_fri_rows<<<(th + 127) / 128, 128, 0, stream>>>(e, j.domain, dpos, j.np, drows);
-            }
-            check_launch();
-            if (j.nflat) {
-                k_gather_digests<<<(unsigned)((j.nflat * 2 + 127) / 128), 128, 0, stream>>>(j.heap, (const uint64_t*)(base + j.o_idx), (uint32_t)j.nflat,
-                                                                                        (uint32_t*)(drows + (size_t)j.np * j.width));
-                check_launch();
-            }
-        }
-        std::vector<uint8_t> host(out_bytes);
-        d2h(host.data(), base + o_out0, out_bytes);
-        for (size_t q = 0; q < reqs.size(); q++) {
-            const Job& j = jobs[q];
-            const uint8_t* h = host.data() + j.o_out;
-            const size_t rb = (size_t)j.np * j.width * 16;
-            reqs[q].rows->assign(h, h + rb);
-            *reqs[q].paths = batch_proof_bytes(j.depth, j.plan, h + rb);
-        }
-    }
-
     // ==========================================================================================================
-    // Prover::prove: the whole pipeline with the channel on the host  
+    // Prover::prove  (SURVEY §3.2).  One GPU: the Fiat-Shamir channel runs on the device (csrc/coin.cuh) — the host enqueues
+    // every stage back to back, waits ONCE on a blocking event, and assembles Proof::to_bytes() from a single download
+    // (transcript, OOD frame, remainder, and for every commitment the rows and full authentication paths at the raw query
+    // positions, from which the host picks what BatchMerkleProof needs after sorting / deduplicating the positions).
     // sharded = true: `cols` / `d_trace_in` hold only this rank's w/G columns and the proof is produced cooperatively by all
-    // ranks of the NCCL communicator (every rank returns the same bytes)
+    // ranks of the NCCL communicator with the channel on the host (every rank returns the same bytes).
     std::vector<uint8_t> prove(const zkb_air_desc* desc, const uint8_t* const* cols, const fe* d_trace_in, uint64_t force_nonce,
                                bool sharded = false) {
         begin(desc);
         t_begin(TS_TOTAL);
+        if (sharded) return prove_sharded(cols, d_trace_in, force_nonce);
+        if (d_trace_in) trace_commit_dev(nullptr, d_trace_in);
+        else { if (!cols) throw InvalidArg("null trace columns"); trace_commit_dev(cols, nullptr); }
+        fs_after_trace_root(d_tree.as<uint32_t>() + 8, nullptr);       // channel.commit_trace; get_constraint_composition_coeffs
+        constraints_eval_dev();
+        constraints_commit_dev();
+        fs_after_constraint_root(d_comp_tree.as<uint32_t>() + 8, nullptr);   // channel.commit_constraints; get_ood_point
+        ood_eval_dev();
+        fs_after_ood(true, nullptr);                                   // send_ood_*; get_deep_composition_coeffs
+        deep_compose_dev();
+        t_begin(TS_FRI);
+        for (uint32_t l = 0; l < fri_layers; l++) {                    // FriProver::build_layers
+            fri_commit_layer_dev();
+            k_fs_fri_root<<<1, 32, 0, stream>>>(dts(), d_fri_tree[l].as<uint32_t>() + 8, l);
+            check_launch();
+            fri_fold_dev();
+        }
+        fri_remainder_dev(true);
+        t_end(TS_FRI);
+        t_begin(TS_GRIND);
+        if (force_nonce) { const unsigned long long v = force_nonce; h2d_small(&dts()->nonce, &v, 8); }
+        else {                                                         // grind_query_seed
+            k_fs_grind<<<(unsigned)sm_count * 8, 256, 0, stream>>>(dts(), air.grinding, 1ull << 44);
+            check_launch();
+        }
+        t_end(TS_GRIND);
+        t_begin(TS_QUERY);
+        const uint32_t q = air.num_queries;
+        k_fs_positions<<<1, ZKB_FS_THREADS, 0, stream>>>(dts(), q, (uint32_t)(air.lde_size() - 1));   // get_query_positions
+        check_launch();
+        {   // TraceLde::query, ConstraintCommitment::query, FriProver::build_proof at the raw positions
+            const uint32_t* dpos = dts()->positions;
+            uint8_t* base = d_fs.as<uint8_t>();
+            for (size_t t = 0; t < fs.trees.size(); t++) {
+                const FsTree& tr = fs.trees[t];
+                const uint32_t th = q * tr.width;
+                fe* drows = (fe*)(base + tr.o_rows);
+                const uint32_t* heap;
+                if (t == 0) { k_gather_lde_rows<<<(th + 127) / 128, 128, 0, stream>>>(lde_mat(), dpos, q, drows); heap = d_tree.as<uint32_t>(); }
+                else if (t == 1) { k_gather_lde_rows<<<(th + 127) / 128, 128, 0, stream>>>(comp_mat(), dpos, q, drows); heap = d_comp_tree.as<uint32_t>(); }
+                else {
+                    const uint32_t l = (uint32_t)t - 2;
+                    const fe* e = l == 0 ? d_deep.as<fe>() : d_fri_evals[l].as<fe>();
+                    k_gather_fri_rows<<<(th + 127) / 128, 128, 0, stream>>>(e, fri_domain(l) / 16, dpos, q, drows);
+                    heap = d_fri_tree[l].as<uint32_t>();
+                }
+                check_launch();
+                const uint32_t pt = q * tr.depth * 2;
+                if (pt) {   // (a one-leaf tree has no authentication nodes)
+                    k_gather_paths<<<(pt + 127) / 128, 128, 0, stream>>>(heap, tr.depth, dpos, q, (1u << tr.depth) - 1u, (uint32_t*)(base + tr.o_paths));
+                    check_launch();
+                }
+            }
+        }
+        t_end(TS_QUERY);
+        t_end(TS_TOTAL);
+        CK(cudaMemcpyAsync(h_out, d_fs.p, fs.host_bytes, cudaMemcpyDeviceToHost, stream));
+        CK(cudaEventRecord(ev_done, stream));
+        CK(cudaEventSynchronize(ev_done));
+        stage = ST_QUERY;
+        return assemble_proof();
+    }
+
+    // Proof assembly from the single download: sort / dedup the positions (get_query_positions), fold them per FRI layer
+    // (fold_positions), select rows, and build every BatchMerkleProof from the full paths gathered on the device — each node of
+    // a batch proof is the sibling of an ancestor of some queried leaf, so it is in one of those paths.
+    std::vector<uint8_t> assemble_proof() {
+        const DevTs* h = reinterpret_cast<const DevTs*>(h_out);
+        if (h->coin_failed) throw std::runtime_error("random coin failed to draw a field element");
+        if (h->nonce == ~0ull) throw std::runtime_error("proof-of-work nonce not found");
+        const uint32_t w = air.w, q = air.num_queries;
+        memcpy(ts.trace_root, h->trace_root, 32); memcpy(ts.constraint_root, h->constraint_root, 32);
+        memcpy(ts.remainder_commitment, h->rem_commit, 32);
+        memcpy(ts.constraint_alpha, &h->alpha, 16); memcpy(ts.z, &h->z, 16); memcpy(ts.deep_alpha, &h->deep_alpha, 16);
+        ts.n_fri_layers = fri_layers;
+        if (h->bad_degree) ts.comp_degree_ok = 0;
+        auto dg = [](const uint32_t* p) { Digest32 d; memcpy(d.b, p, 32); return d; };
+        parts.commitments.push_back(dg(h->trace_root));
+        parts.commitments.push_back(dg(h->constraint_root));
+        for (uint32_t l = 0; l < fri_layers; l++) {
+            parts.commitments.push_back(dg(h->fri_roots[l]));
+            memcpy(ts.fri_roots[l], h->fri_roots[l], 32); memcpy(ts.fri_alphas[l], &h->fri_alpha[l], 16);
+        }
+        parts.commitments.push_back(dg(h->rem_commit));
+        const HF* frame = reinterpret_cast<const HF*>(h_out + fs.o_ood);
+        parts.ood_trace_interleaved.resize(2 * (size_t)w);   // [T_0(z), T_0(zg), T_1(z), ...]  [A.5]
+        for (uint32_t j = 0; j < w; j++) { parts.ood_trace_interleaved[2 * j] = frame[j]; parts.ood_trace_interleaved[2 * j + 1] = frame[w + j]; }
+        parts.ood_h.assign(frame + 2 * (size_t)w, frame + 2 * (size_t)w + c);
+        const uint32_t rs = (uint32_t)((air.lde_size() >> (4 * fri_layers)) / air.blowup);
+        const HF* rem = reinterpret_cast<const HF*>(h_out + fs.o_rem);
+        parts.remainder.assign(rem, rem + rs);
+        parts.nonce = h->nonce; ts.pow_nonce = h->nonce;
+        std::vector<uint32_t> raw(h->positions, h->positions + q);
+        positions = raw;
+        std::sort(positions.begin(), positions.end());
+        positions.erase(std::unique(positions.begin(), positions.end()), positions.end());
+        parts.n_unique = (uint32_t)positions.size();
+        ts.n_positions = parts.n_unique;
+        for (size_t i = 0; i < positions.size() && i < 256; i++) ts.positions[i] = positions[i];
+        // one commitment: rows of `pos` (each found among the raw positions reduced by `mask`) + batch proof
+        auto open = [&](const FsTree& tr, const std::vector<uint32_t>& pos, uint32_t mask, std::vector<uint8_t>& rows, std::vector<uint8_t>& paths) {
+            const uint8_t* hrows = h_out + tr.o_rows;
+            const uint8_t* hpaths = h_out + tr.o_paths;
+            const size_t rb = (size_t)tr.width * 16;
+            std::map<uint32_t, uint32_t> first;   // reduced position -> a raw index that carries it
+            for (uint32_t i = 0; i < q; i++) first.emplace(raw[i] & mask, i);
+            rows.resize(pos.size() * rb);
+            for (size_t i = 0; i < pos.size(); i++) memcpy(&rows[i * rb], hrows + (size_t)first.at(pos[i]) * rb, rb);
+            std::map<uint64_t, const uint8_t*> node;   // heap index -> digest, from the full paths
+            for (uint32_t i = 0; i < q; i++)
+                for (uint32_t lv = 0; lv < tr.depth; lv++)
+                    node.emplace(((((uint64_t)1 << tr.depth) + (raw[i] & mask)) >> lv) ^ 1ull, hpaths + ((size_t)i * tr.depth + lv) * 32);
+            std::vector<std::vector<uint64_t>> plan = plan_batch_proof(tr.depth, pos);
+            std::vector<uint8_t> gathered;
+            for (auto& v : plan) for (uint64_t hi : v) { const uint8_t* d = node.at(hi); gathered.insert(gathered.end(), d, d + 32); }
+            paths = batch_proof_bytes(tr.depth, plan, gathered.data());
+        };
+        open(fs.trees[0], positions, (uint32_t)(air.lde_size() - 1), parts.trace_rows, parts.trace_paths);
+        open(fs.trees[1], positions, (uint32_t)(air.lde_size() - 1), parts.comp_rows, parts.comp_paths);
+        parts.fri_rows.resize(fri_layers); parts.fri_paths.resize(fri_layers);
+        std::vector<uint32_t> fpos = positions;
+        uint64_t dom = air.lde_size();
+        for (uint32_t l = 0; l < fri_layers; l++) {
+            fpos = fold_positions(fpos, dom, 16);
+            dom /= 16;
+            open(fs.trees[2 + l], fpos, (uint32_t)(dom - 1), parts.fri_rows[l], parts.fri_paths[l]);
+        }
+        return serialize_proof(air, parts);
+    }
+
+    // column-sharded proof: the channel stays on the host (every rank replays it identically between the collectives)
+    std::vector<uint8_t> prove_sharded(const uint8_t* const* cols, const fe* d_trace_in, uint64_t force_nonce) {
         uint8_t root[32];
-        if (sharded) trace_commit_mg(cols, d_trace_in, root);
-        else if (d_trace_in) trace_commit_device(d_trace_in, root);
-        else trace_commit_host(cols, root);
+        trace_commit_mg(cols, d_trace_in, root);
         coin.reseed(root);                                   // channel.commit_trace
         HF alpha = coin.draw();                              // get_constraint_composition_coeffs
         alpha.to_bytes(ts.constraint_alpha);
@@ -1218,17 +1402,9 @@ struct zkb_ctx {
                 fpos[l] = fold_positions(l ? fpos[l - 1] : positions, dom, 16);
                 dom /= 16;
             }
-            if (!mg_active) {
-                std::vector<QueryReq> reqs;
-                for (uint32_t l = 0; l < fri_layers; l++) reqs.push_back({2 + l, &fpos[l], &parts.fri_rows[l], &parts.fri_paths[l]});
-                reqs.push_back({0, &positions, &parts.trace_rows, &parts.trace_paths});
-                reqs.push_back({1, &positions, &parts.comp_rows, &parts.comp_paths});
-                query_all(reqs);
-            } else {
-                for (uint32_t l = 0; l < fri_layers; l++) query(2 + l, fpos[l], parts.fri_rows[l], parts.fri_paths[l]);
-                query(0, positions, parts.trace_rows, parts.trace_paths);
-                query(1, positions, parts.comp_rows, parts.comp_paths);
-            }
+            for (uint32_t l = 0; l < fri_layers; l++) query(2 + l, fpos[l], parts.fri_rows[l], parts.fri_paths[l]);
+            query(0, positions, parts.trace_rows, parts.trace_paths);
+            query(1, positions, parts.comp_rows, parts.comp_paths);
         }
         t_end(TS_QUERY);
         t_end(TS_TOTAL);
