@@ -440,10 +440,11 @@ def main():
     alg = algorithmic_bytes(n, w, beta, ce, c)
 
     # ---- contexts: one per in-flight proof, each on its own stream with its own device buffers --------------------------------
-    # default: four proofs in flight per GPU (62.7 vs 61.7 proofs/s with two); two when the host has fewer than 8 cores per rank,
-    # because every lane is a host thread that spins in the CUDA runtime while it waits for the device
+    # default: four proofs in flight per GPU; two when the host has fewer than 4 cores per rank.  A lane's host thread enqueues a whole
+    # proof (the Fiat-Shamir channel runs on the device) and then sleeps on a blocking CUDA event, so lanes do not need a spinning
+    # core each any more (round 1 had to drop to two lanes on the 32-core 8-GPU box)
     if args.inflight <= 0:
-        args.inflight = 4 if (os.cpu_count() or 1) >= 8 * world else 2
+        args.inflight = 4 if (os.cpu_count() or 1) >= 4 * world else 2
     inflight = 1 if sharded else max(1, args.inflight)
     if 2.4 * n * beta * w_local * 16 * inflight > 100e9:  # LDE + NTT scratch + polys per lane must fit the 180 GB of HBM
         inflight = 1

@@ -156,7 +156,8 @@ int32_t zkb_fri_remainder(zkb_ctx* ctx, uint8_t* coeffs_out, uint64_t* n_coeffs_
 /* ProverChannel::grind_query_seed: smallest nonce >= 1 with >= bits trailing zeros: K10 */
 int32_t zkb_grind(zkb_ctx* ctx, const uint8_t seed[32], uint32_t bits, uint64_t* nonce_out);
 /* TraceLde::query / ConstraintCommitment::query / FriProver::build_proof: K11.
- * which: 0 = trace, 1 = constraint composition, 2+l = FRI layer l (positions already folded by the caller).
+ * which: 0 = trace (any time after zkb_trace_commit), 1 = constraint composition (after zkb_constraints_commit),
+ *        2+l = FRI layer l (after zkb_fri_remainder; positions already folded by the caller).
  * rows_out: n_pos rows, row-major; proof_out: BatchMerkleProof::to_bytes(), allocated by the library. */
 int32_t zkb_query(zkb_ctx* ctx, uint32_t which, const uint32_t* positions, uint32_t n_pos, uint8_t* rows_out,
                   uint8_t** proof_out, uint64_t* proof_len);

@@ -66,12 +66,14 @@ extern "C" {
                             proof_out: *mut *mut u8, proof_len: *mut u64, transcript: *mut zkb_transcript) -> i32;
     pub fn zkb_prove_batch(lanes: *const *mut zkb_ctx, n_lanes: u32, airs: *const *const zkb_air_desc, cols: *const *const *const u8,
                            count: u32, proofs_out: *mut *mut u8, lens_out: *mut u64) -> i32;
-    pub fn zkb_training_trace_device(ctx: *mut zkb_ctx, raw_rows: *const u8, n_raw: u32, half: u32, n: u64, seed: u64,
+    /// key32: 32 bytes of ChaCha20 key for the blinding masks, or null = OS entropy (what rand::thread_rng() does)
+    pub fn zkb_training_trace_device(ctx: *mut zkb_ctx, raw_rows: *const u8, n_raw: u32, half: u32, n: u64, key32: *const u8,
                                      d_out: *mut *mut c_void, first_row_out: *mut u8, last_row_out: *mut u8) -> i32;
 
     pub fn zkb_begin(ctx: *mut zkb_ctx, air: *const zkb_air_desc) -> i32;
     pub fn zkb_trace_commit(ctx: *mut zkb_ctx, cols: *const *const u8, root_out: *mut u8) -> i32;
     pub fn zkb_trace_read_frame(ctx: *mut zkb_ctx, lde_step: u64, current_out: *mut u8, next_out: *mut u8) -> i32;
+    pub fn zkb_trace_read_frames(ctx: *mut zkb_ctx, lde_steps: *const u64, count: u32, current_out: *mut u8, next_out: *mut u8) -> i32;
     pub fn zkb_trace_polys_read(ctx: *mut zkb_ctx, out: *mut u8) -> i32;
     pub fn zkb_constraints_eval(ctx: *mut zkb_ctx, alpha: *const u8, evals_out: *mut u8) -> i32;
     pub fn zkb_constraints_commit(ctx: *mut zkb_ctx, root_out: *mut u8) -> i32;

@@ -105,18 +105,9 @@ def _staged_values(ctx, oracle, air, data, ce):
     assert ev.raw == comp, "constraint evaluations differ"
     ctx.check(lib.zkb_constraints_commit(h, root))
     assert root.raw == bytes(ts.constraint_root)
-    ctx.check(lib.zkb_ood_eval(h, bytes(ts.z), None, None, None))
-    ctx.check(lib.zkb_deep_compose(h, bytes(ts.deep_alpha)))
-    nl = C.c_uint32()
-    ctx.check(lib.zkb_fri_num_layers(h, C.byref(nl)))
-    for l in range(nl.value):
-        ctx.check(lib.zkb_fri_commit_layer(h, root))
-        assert root.raw == bytes(ts.fri_roots[l])
-        ctx.check(lib.zkb_fri_fold(h, bytes(ts.fri_alphas[l])))
-    rem, cnt = C.create_string_buffer(16 * 256), C.c_uint64()
-    ctx.check(lib.zkb_fri_remainder(h, rem, C.byref(cnt), root))
-    assert root.raw == bytes(ts.remainder_commitment)
-    # TraceLde::query / ConstraintCommitment::query against the Queries sections of the oracle's proof
+    # TraceLde::query / ConstraintCommitment::query against the Queries sections of the oracle's proof — asked right after the
+    # constraint commitment, as Winterfell's own generate_proof does when only the associated types are swapped (OOD, DEEP and
+    # FRI then run on the host), and before this test drives the remaining device stages
     c = 6 if air["air_id"] == 3 else 1
     t_rows, t_paths, c_rows, c_paths = _parse_queries(ref_proof, w, c)
     pos = (C.c_uint32 * ts.n_positions)(*list(ts.positions)[:ts.n_positions])
@@ -128,6 +119,17 @@ def _staged_values(ctx, oracle, air, data, ce):
         lib.zkb_free(po)
         assert rows.raw == want_rows, f"queried rows of commitment {which} differ"
         assert paths == want_paths, f"batch Merkle proof of commitment {which} differs"
+    ctx.check(lib.zkb_ood_eval(h, bytes(ts.z), None, None, None))
+    ctx.check(lib.zkb_deep_compose(h, bytes(ts.deep_alpha)))
+    nl = C.c_uint32()
+    ctx.check(lib.zkb_fri_num_layers(h, C.byref(nl)))
+    for l in range(nl.value):
+        ctx.check(lib.zkb_fri_commit_layer(h, root))
+        assert root.raw == bytes(ts.fri_roots[l])
+        ctx.check(lib.zkb_fri_fold(h, bytes(ts.fri_alphas[l])))
+    rem, cnt = C.create_string_buffer(16 * 256), C.c_uint64()
+    ctx.check(lib.zkb_fri_remainder(h, rem, C.byref(cnt), root))
+    assert root.raw == bytes(ts.remainder_commitment)
 
 
 def test_staged_values_aggregation(gpu_ctx, oracle):

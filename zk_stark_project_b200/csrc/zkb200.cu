@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 #include <sys/random.h>
 #include <nccl.h>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <functional>
@@ -1219,7 +1220,10 @@ struct zkb_ctx {
     // ranks of the NCCL communicator with the channel on the host (every rank returns the same bytes).
     std::vector<uint8_t> prove(const zkb_air_desc* desc, const uint8_t* const* cols, const fe* d_trace_in, uint64_t force_nonce,
                                bool sharded = false) {
+        static const bool host_prof = getenv("ZKB_HOST_PROFILE") != nullptr;   // diagnostics: host phases of a proof on stderr
+        const auto hp0 = std::chrono::steady_clock::now();
         begin(desc);
+        const auto hp1 = std::chrono::steady_clock::now();
         t_begin(TS_TOTAL);
         if (sharded) return prove_sharded(cols, d_trace_in, force_nonce);
         if (d_trace_in) trace_commit_dev(nullptr, d_trace_in);
@@ -1278,10 +1282,21 @@ struct zkb_ctx {
         t_end(TS_QUERY);
         t_end(TS_TOTAL);
         CK(cudaMemcpyAsync(h_out, d_fs.p, fs.host_bytes, cudaMemcpyDeviceToHost, stream));
-        CK(cudaEventRecord(ev_done, stream));
-        CK(cudaEventSynchronize(ev_done));
+        const auto hp2 = std::chrono::steady_clock::now();
+        // small proofs: spin on the stream (a blocking wait costs a wake-up, tens of microseconds, which is a large part of a
+        // sub-millisecond proof); large proofs: sleep on the event so that a lane does not burn a host core while the GPU works
+        if ((air.lde_size() * air.w) >> 22) { CK(cudaEventRecord(ev_done, stream)); CK(cudaEventSynchronize(ev_done)); }
+        else CK(cudaStreamSynchronize(stream));
+        const auto hp3 = std::chrono::steady_clock::now();
         stage = ST_QUERY;
-        return assemble_proof();
+        std::vector<uint8_t> out = assemble_proof();
+        if (host_prof) {
+            const auto hp4 = std::chrono::steady_clock::now();
+            auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+            fprintf(stderr, "[zkb host] begin %.1f us, enqueue %.1f us, wait %.1f us, assemble %.1f us, launches so far %llu\n", us(hp0, hp1), us(hp1, hp2),
+                    us(hp2, hp3), us(hp3, hp4), (unsigned long long)launches);
+        }
+        return out;
     }
 
     // Proof assembly from the single download: sort / dedup the positions (get_query_positions), fold them per FRI layer
@@ -1325,17 +1340,27 @@ struct zkb_ctx {
             const uint8_t* hrows = h_out + tr.o_rows;
             const uint8_t* hpaths = h_out + tr.o_paths;
             const size_t rb = (size_t)tr.width * 16;
-            std::map<uint32_t, uint32_t> first;   // reduced position -> a raw index that carries it
-            for (uint32_t i = 0; i < q; i++) first.emplace(raw[i] & mask, i);
+            std::vector<std::pair<uint32_t, uint32_t>> first(q);   // (reduced position, a raw index that carries it), sorted
+            for (uint32_t i = 0; i < q; i++) first[i] = {raw[i] & mask, i};
+            std::sort(first.begin(), first.end());
+            auto raw_index_in = [&](uint64_t lo, uint64_t hi_excl) -> uint32_t {   // a raw index whose reduced position is in [lo, hi)
+                auto it = std::lower_bound(first.begin(), first.end(), std::make_pair((uint32_t)lo, 0u));
+                if (it == first.end() || it->first >= hi_excl) throw std::runtime_error("internal error: opening not gathered");
+                return it->second;
+            };
             rows.resize(pos.size() * rb);
-            for (size_t i = 0; i < pos.size(); i++) memcpy(&rows[i * rb], hrows + (size_t)first.at(pos[i]) * rb, rb);
-            std::map<uint64_t, const uint8_t*> node;   // heap index -> digest, from the full paths
-            for (uint32_t i = 0; i < q; i++)
-                for (uint32_t lv = 0; lv < tr.depth; lv++)
-                    node.emplace(((((uint64_t)1 << tr.depth) + (raw[i] & mask)) >> lv) ^ 1ull, hpaths + ((size_t)i * tr.depth + lv) * 32);
+            for (size_t i = 0; i < pos.size(); i++) memcpy(&rows[i * rb], hrows + (size_t)raw_index_in(pos[i], (uint64_t)pos[i] + 1) * rb, rb);
+            // node `hi` of the heap sits `lv` levels above the leaves and is the sibling of an ancestor of some queried leaf: that
+            // leaf lies under hi ^ 1, and its gathered path holds `hi` at position lv
             std::vector<std::vector<uint64_t>> plan = plan_batch_proof(tr.depth, pos);
             std::vector<uint8_t> gathered;
-            for (auto& v : plan) for (uint64_t hi : v) { const uint8_t* d = node.at(hi); gathered.insert(gathered.end(), d, d + 32); }
+            for (auto& v : plan)
+                for (uint64_t hi : v) {
+                    const uint32_t lv = tr.depth - (63u - (uint32_t)__builtin_clzll(hi));
+                    const uint64_t anc = hi ^ 1ull, lo = (anc << lv) - ((uint64_t)1 << tr.depth);
+                    const uint8_t* d = hpaths + ((size_t)raw_index_in(lo, lo + ((uint64_t)1 << lv)) * tr.depth + lv) * 32;
+                    gathered.insert(gathered.end(), d, d + 32);
+                }
             paths = batch_proof_bytes(tr.depth, plan, gathered.data());
         };
         open(fs.trees[0], positions, (uint32_t)(air.lde_size() - 1), parts.trace_rows, parts.trace_paths);
@@ -1600,7 +1625,11 @@ int32_t zkb_grind(zkb_ctx* ctx, const uint8_t seed[32], uint32_t bits, uint64_t*
 int32_t zkb_query(zkb_ctx* ctx, uint32_t which, const uint32_t* positions, uint32_t n_pos, uint8_t* rows_out, uint8_t** proof_out,
                   uint64_t* proof_len) {
     return guarded(ctx, [&] {
-        if (ctx->stage < ST_FRI_DONE) throw StateError("zkb_query: the FRI commit phase is not finished");
+        // a commitment can be opened as soon as it exists: Winterfell's own generate_proof (associated-type integration) runs
+        // DEEP and FRI on the host and then calls TraceLde::query / ConstraintCommitment::query
+        if (which == 0 && ctx->stage < ST_TRACE) throw StateError("zkb_query: the trace is not committed");
+        if (which == 1 && ctx->stage < ST_COMP) throw StateError("zkb_query: the constraint composition is not committed");
+        if (which >= 2 && ctx->stage < ST_FRI_DONE) throw StateError("zkb_query: the FRI commit phase is not finished");
         if (!positions) throw InvalidArg("null positions");
         std::vector<uint32_t> pos(positions, positions + n_pos);
         std::vector<uint8_t> rows, paths;
