@@ -1,5 +1,7 @@
 // Butterfly throughput of f128 multiplier variants on sm_100a (register-resident, no memory traffic):
-//   A: mad-chain folds with C = {0xFFFFFFFF, 0x2CFF}                       (csrc/f128.cuh as shipped)
+//   A: mad-chain folds with C = {0xFFFFFFFF, 0x2CFF}                       (round 1)
+//   E: folds with K = 0x2D00, 2^128 = K*2^32 - 1                           (csrc/f128.cuh fe_reduce256 as shipped)
+//   F: twiddle held as four pre-shifted copies, no first fold              (csrc/f128.cuh fe_mul_pre4, the NTT's multiplier)
 //   B: hi*C = ((hi*45) << 40) - hi with funnel shifts                       (ALU-heavy)
 //   C: hi*C = (hi << 32) - hi + ((hi*0x2CFF) << 32): limb shift/sub + 4 IMAD.WIDE by the small constant
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/mul_variants tools/mul_variants.cu && ./tools/mul_variants
@@ -33,11 +35,11 @@ __global__ void __launch_bounds__(256) k(fe* io, const fe* tw, int iters) {
     for (int u = 0; u < UNITS; u++) { x[u] = fe_load(io + (size_t)t * 2 * UNITS + 2 * u); y[u] = fe_load(io + (size_t)t * 2 * UNITS + 2 * u + 1); }
     const fe w = fe_load(tw + (threadIdx.x & 31));
     fe4 w4;
-    if (V == 5) { fe sh = fe_zero(); sh.x[1] = 1; w4.w[0] = fe_canon(w, 0); for (int i = 1; i < 4; i++) w4.w[i] = fe_mul(w4.w[i - 1], sh); }
+    if (V == 5) w4 = fe4_from(fe_canon(w, 0));
     for (int i = 0; i < iters; i++) {
 #pragma unroll
         for (int u = 0; u < UNITS; u++) {
-            const fe v = V == 5 ? mul_pre4(y[u], w4) : mulv<(V == 3 ? 0 : V)>(y[u], w);
+            const fe v = V == 5 ? fe_mul_pre4(y[u], w4) : mulv<(V == 3 ? 0 : V)>(y[u], w);
             const fe a = x[u];
             x[u] = V == 3 ? add_lazy(a, v) : fe_add(a, v);
             y[u] = fe_sub(a, v);
@@ -74,11 +76,11 @@ int main() {
     for (int i = 0; i < 64; i++) host_tw[i] = 0x9E3779B97F4A7C15ULL * (i + 1) >> (i & 1);
     cudaMemcpy(tw, host_tw, 512, cudaMemcpyHostToDevice);
     unsigned long long ref[2] = {0, 0};
-    run<0>("A mad-chain folds (shipped)", io, tw, ref, false);
+    run<0>("A mad-chain folds (round 1)", io, tw, ref, false);
     run<1>("B (hi*45)<<40 - hi", io, tw, ref, true);
     run<2>("C (hi<<32) - hi + hi*c1<<32", io, tw, ref, true);
-    run<3>("D shipped mul, non-canonical sums", io, tw, ref, true);
-    run<4>("E k = 0x2D00 fold (no *0xFFFFFFFF)", io, tw, ref, true);
-    run<5>("F 4 pre-shifted twiddle copies", io, tw, ref, true);
+    run<3>("D round-1 mul, non-canonical sums", io, tw, ref, true);
+    run<4>("E K = 0x2D00 fold (shipped fe_mul)", io, tw, ref, true);
+    run<5>("F 4 pre-shifted copies (shipped NTT)", io, tw, ref, true);
     return 0;
 }

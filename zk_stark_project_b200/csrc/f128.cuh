@@ -177,6 +177,73 @@ __device__ __forceinline__ fe fe_mul(const fe& a, const fe& b) {
     mul_wide(a, b, w);
     return fe_reduce256(w);
 }
+// ---- multiplication by a twiddle that is known in advance --------------------------------------------------------------------
+// A twiddle w is used for many butterflies (every column of a tile, several butterflies of a unit), so it pays to hold it as four
+// pre-shifted copies W_i = w * 2^(32 i) mod p: x * w = sum_i x_i * W_i is then four ALIGNED 32 x 128-bit rows (16 IMAD.WIDE) whose
+// sum is < 2^162 — the 128-bit first fold of fe_reduce256 disappears and only a 34-bit top is folded.  69 instead of 87 SASS
+// instructions per butterfly (tools/mul_variants.cu variant F, profiles/r2_mul_variants.txt).
+struct __align__(16) fe4 { fe w[4]; };
+
+// a * 2^32 mod p:  (a << 32) = [0, a0, a1, a2] + a3 * 2^128,  and  a3 * 2^128 = ((a3 * K) << 32) - a3  (K = 0x2D00)
+__device__ __forceinline__ fe fe_shl32(const fe& a) {
+    const uint32_t k = 0x2D00u;
+    uint32_t q0, q1, s1, s2, s3, cy, bw;
+    fe r;
+    asm("{\n\t"
+        "mul.lo.u32 %0, %14, %15;\n\t mul.hi.u32 %1, %14, %15;\n\t"
+        "add.cc.u32 %2, %11, %0;\n\t addc.cc.u32 %3, %12, %1;\n\t addc.cc.u32 %4, %13, 0;\n\t addc.u32 %5, 0, 0;\n\t"
+        "sub.cc.u32 %6, 0, %14;\n\t subc.cc.u32 %7, %2, 0;\n\t subc.cc.u32 %8, %3, 0;\n\t subc.cc.u32 %9, %4, 0;\n\t subc.u32 %10, 0, 0;\n\t"
+        "}"
+        : "=&r"(q0), "=&r"(q1), "=&r"(s1), "=&r"(s2), "=&r"(s3), "=&r"(cy), "=&r"(r.x[0]), "=&r"(r.x[1]), "=&r"(r.x[2]), "=&r"(r.x[3]), "=&r"(bw)
+        : "r"(a.x[0]), "r"(a.x[1]), "r"(a.x[2]), "r"(a.x[3]), "r"(k));
+    return fe_canon(r, cy + bw);   // bw is 0 or 0xFFFFFFFF; the true value is in [0, 2^128 + 2^78): net wrap 0 or 1
+}
+__device__ __forceinline__ fe4 fe4_from(const fe& w) {
+    fe4 t;
+    t.w[0] = w; t.w[1] = fe_shl32(w); t.w[2] = fe_shl32(t.w[1]); t.w[3] = fe_shl32(t.w[2]);
+    return t;
+}
+// x * w for w given as its four pre-shifted copies; x may be any 128-bit value, the copies must be canonical
+__device__ __forceinline__ fe fe_mul_pre4(const fe& x, const fe4& t) {
+    const uint32_t k = 0x2D00u;
+    uint32_t e0, e1, e2, e3, e4, o0, o1, o2, o3, o4;
+    asm("{\n\t"
+        "mul.lo.u32 %0, %10, %14;\n\t mul.hi.u32 %1, %10, %14;\n\t mul.lo.u32 %2, %10, %16;\n\t mul.hi.u32 %3, %10, %16;\n\t"
+        "mul.lo.u32 %5, %10, %15;\n\t mul.hi.u32 %6, %10, %15;\n\t mul.lo.u32 %7, %10, %17;\n\t mul.hi.u32 %8, %10, %17;\n\t"
+        "mad.lo.cc.u32 %0, %11, %18, %0;\n\t madc.hi.cc.u32 %1, %11, %18, %1;\n\t madc.lo.cc.u32 %2, %11, %20, %2;\n\t madc.hi.cc.u32 %3, %11, %20, %3;\n\t"
+        "addc.u32 %4, 0, 0;\n\t"
+        "mad.lo.cc.u32 %5, %11, %19, %5;\n\t madc.hi.cc.u32 %6, %11, %19, %6;\n\t madc.lo.cc.u32 %7, %11, %21, %7;\n\t madc.hi.cc.u32 %8, %11, %21, %8;\n\t"
+        "addc.u32 %9, 0, 0;\n\t"
+        "mad.lo.cc.u32 %0, %12, %22, %0;\n\t madc.hi.cc.u32 %1, %12, %22, %1;\n\t madc.lo.cc.u32 %2, %12, %24, %2;\n\t madc.hi.cc.u32 %3, %12, %24, %3;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "mad.lo.cc.u32 %5, %12, %23, %5;\n\t madc.hi.cc.u32 %6, %12, %23, %6;\n\t madc.lo.cc.u32 %7, %12, %25, %7;\n\t madc.hi.cc.u32 %8, %12, %25, %8;\n\t"
+        "addc.u32 %9, %9, 0;\n\t"
+        "mad.lo.cc.u32 %0, %13, %26, %0;\n\t madc.hi.cc.u32 %1, %13, %26, %1;\n\t madc.lo.cc.u32 %2, %13, %28, %2;\n\t madc.hi.cc.u32 %3, %13, %28, %3;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "mad.lo.cc.u32 %5, %13, %27, %5;\n\t madc.hi.cc.u32 %6, %13, %27, %6;\n\t madc.lo.cc.u32 %7, %13, %29, %7;\n\t madc.hi.cc.u32 %8, %13, %29, %8;\n\t"
+        "addc.u32 %9, %9, 0;\n\t"
+        "}"
+        : "=&r"(e0), "=&r"(e1), "=&r"(e2), "=&r"(e3), "=&r"(e4), "=&r"(o0), "=&r"(o1), "=&r"(o2), "=&r"(o3), "=&r"(o4)
+        : "r"(x.x[0]), "r"(x.x[1]), "r"(x.x[2]), "r"(x.x[3]),
+          "r"(t.w[0].x[0]), "r"(t.w[0].x[1]), "r"(t.w[0].x[2]), "r"(t.w[0].x[3]), "r"(t.w[1].x[0]), "r"(t.w[1].x[1]), "r"(t.w[1].x[2]), "r"(t.w[1].x[3]),
+          "r"(t.w[2].x[0]), "r"(t.w[2].x[1]), "r"(t.w[2].x[2]), "r"(t.w[2].x[3]), "r"(t.w[3].x[0]), "r"(t.w[3].x[1]), "r"(t.w[3].x[2]), "r"(t.w[3].x[3]));
+    // r = even + (odd << 32): six limbs, r5:r4 < 2^34
+    uint32_t r1, r2, r3, r4, r5;
+    asm("add.cc.u32 %0, %5, %9;\n\t addc.cc.u32 %1, %6, %10;\n\t addc.cc.u32 %2, %7, %11;\n\t addc.cc.u32 %3, %8, %12;\n\t addc.u32 %4, %13, 0;"
+        : "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5)
+        : "r"(e1), "r"(e2), "r"(e3), "r"(e4), "r"(o0), "r"(o1), "r"(o2), "r"(o3), "r"(o4));
+    uint32_t q0, q1, w0, w1, w2, cy;
+    fe out;
+    asm("{\n\t"
+        "mul.lo.u32 %0, %10, %12;\n\t mul.hi.u32 %1, %10, %12;\n\t mad.lo.u32 %1, %11, %12, %1;\n\t"
+        "sub.cc.u32 %2, 0, %10;\n\t subc.cc.u32 %3, %0, %11;\n\t subc.u32 %4, %1, 0;\n\t"
+        "add.cc.u32 %5, %13, %2;\n\t addc.cc.u32 %6, %14, %3;\n\t addc.cc.u32 %7, %15, %4;\n\t addc.cc.u32 %8, %16, 0;\n\t addc.u32 %9, 0, 0;\n\t"
+        "}"
+        : "=&r"(q0), "=&r"(q1), "=&r"(w0), "=&r"(w1), "=&r"(w2), "=&r"(out.x[0]), "=&r"(out.x[1]), "=&r"(out.x[2]), "=&r"(out.x[3]), "=&r"(cy)
+        : "r"(r4), "r"(r5), "r"(k), "r"(e0), "r"(r1), "r"(r2), "r"(r3));
+    return fe_canon(out, cy);
+}
+
 // 128-bit square -> 256 bits with 10 wide products instead of 16: the six off-diagonal products are summed once, doubled by a
 // one-bit funnel shift, and the four squares added on top
 __device__ __forceinline__ void sqr_wide(const fe& a, uint32_t r[8]) {

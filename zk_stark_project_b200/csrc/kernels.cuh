@@ -117,36 +117,45 @@ struct NttPass {
 
 __device__ __forceinline__ uint32_t bitrev(uint32_t v, uint32_t bits) { return bits == 0 ? 0u : (__brev(v) >> (32 - bits)); }
 
-// RHO consecutive DIT layers (lam0, lam0 + RHO] of one column, done in registers: the 2^RHO elements of a unit sit at
+// RHO consecutive DIT layers (lam0, lam0 + RHO] of NC columns, done in registers: the 2^RHO elements of a unit sit at
 // positions base + d * 2^lam0.  Layer lam uses tw[2^(lam-1) - 1 + (p0 mod 2^(lam-1))] for the pair (p0, p0 + 2^(lam-1)).
-template <int RHO>
-__device__ __forceinline__ void ntt_unit(fe* __restrict__ col, const uint32_t rs, const fe* __restrict__ tw,
+// Twiddles are held as four pre-shifted copies (fe4, f128.cuh): one 64-byte load serves NC * 2^(RHO-1-s) butterflies of layer s.
+// The NC columns of a thread are `cstride` apart so that the threads of a quarter-warp touch one contiguous 128-byte run.
+template <int RHO, int NC>
+__device__ __forceinline__ void ntt_unit(fe* __restrict__ col, const uint32_t rs, const uint32_t cstride, const fe4* __restrict__ tw,
                                          const uint32_t base, const uint32_t lam0) {
     constexpr int R = 1 << RHO;
-    fe x[R];
+    fe x[NC][R];
     const uint32_t step = rs << lam0;
     fe* p = col + base * rs;
 #pragma unroll
-    for (int d = 0; d < R; d++) x[d] = p[d * step];
+    for (int c = 0; c < NC; c++)
+#pragma unroll
+        for (int d = 0; d < R; d++) x[c][d] = p[d * step + c * cstride];
     const uint32_t base_low = base & ((1u << lam0) - 1u);
 #pragma unroll
     for (int s = 0; s < RHO; s++) {
-        const fe* twl = tw + ((1u << (lam0 + s)) - 1u) + base_low;
+        const fe4* twl = tw + ((1u << (lam0 + s)) - 1u) + base_low;
 #pragma unroll
         for (int t = 0; t < (1 << s); t++) {
-            const fe w = twl[(uint32_t)t << lam0];
+            const fe4 w = twl[(uint32_t)t << lam0];
 #pragma unroll
             for (int g = 0; g < (R >> (s + 1)); g++) {
                 const int d0 = g * (2 << s) + t, d1 = d0 + (1 << s);
-                const fe u = x[d0];
-                const fe v = fe_mul(x[d1], w);
-                x[d0] = fe_add(u, v);
-                x[d1] = fe_sub(u, v);
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    const fe u = x[c][d0];
+                    const fe v = fe_mul_pre4(x[c][d1], w);
+                    x[c][d0] = fe_add(u, v);
+                    x[c][d1] = fe_sub(u, v);
+                }
             }
         }
     }
 #pragma unroll
-    for (int d = 0; d < R; d++) p[d * step] = x[d];
+    for (int c = 0; c < NC; c++)
+#pragma unroll
+        for (int d = 0; d < R; d++) p[d * step + c * cstride] = x[c][d];
 }
 
 // twiddle q of the tile (coset k, t_low) of a pass: layer lam = floor(log2(q + 1)) + 1, position th = q + 1 - 2^(lam-1)
@@ -177,24 +186,92 @@ __global__ void k_build_twiddles(const NttPass p, fe* __restrict__ table) {
     fe_store(table + id, ntt_twiddle(p, tile >> p.a, tile & ((1u << p.a) - 1u), q));
 }
 
+// the same for ONE column with plain (single-copy) twiddles: narrow tiles (1-2 columns) reuse a twiddle too rarely for the
+// three shift-folds of fe4_from to pay
 template <int RHO>
-__device__ __forceinline__ void ntt_round(fe* sm, const fe* tw, uint32_t rs, uint32_t log_cj, uint32_t logS, uint32_t lam0) {
+__device__ __forceinline__ void ntt_unit_plain(fe* __restrict__ col, const uint32_t rs, const fe* __restrict__ tw, const uint32_t base, const uint32_t lam0) {
+    constexpr int R = 1 << RHO;
+    fe x[R];
+    const uint32_t step = rs << lam0;
+    fe* p = col + base * rs;
+#pragma unroll
+    for (int d = 0; d < R; d++) x[d] = p[d * step];
+    const uint32_t base_low = base & ((1u << lam0) - 1u);
+#pragma unroll
+    for (int s = 0; s < RHO; s++) {
+        const fe* twl = tw + ((1u << (lam0 + s)) - 1u) + base_low;
+#pragma unroll
+        for (int t = 0; t < (1 << s); t++) {
+            const fe w = twl[(uint32_t)t << lam0];
+#pragma unroll
+            for (int g = 0; g < (R >> (s + 1)); g++) {
+                const int d0 = g * (2 << s) + t, d1 = d0 + (1 << s);
+                const fe u = x[d0];
+                const fe v = fe_mul(x[d1], w);
+                x[d0] = fe_add(u, v);
+                x[d1] = fe_sub(u, v);
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < R; d++) p[d * step] = x[d];
+}
+template <int RHO>
+__device__ __forceinline__ void ntt_round_plain(fe* sm, const fe* tw, uint32_t rs, uint32_t log_cj, uint32_t logS, uint32_t lam0) {
     const uint32_t cj_mask = (1u << log_cj) - 1u;
     const uint32_t units = (1u << (logS - RHO)) << log_cj;
     for (uint32_t idx = threadIdx.x; idx < units; idx += blockDim.x) {
         const uint32_t jj = idx & cj_mask, u = idx >> log_cj;
         const uint32_t base = (u & ((1u << lam0) - 1u)) + ((u >> lam0) << (lam0 + RHO));
-        ntt_unit<RHO>(sm + jj, rs, tw, base, lam0);
+        ntt_unit_plain<RHO>(sm + jj, rs, tw, base, lam0);
+    }
+}
+__device__ __forceinline__ void ntt_rounds_plain(fe* sm, const fe* tw, uint32_t rs, uint32_t log_cj, uint32_t logS) {
+    for (uint32_t lam0 = 0; lam0 < logS;) {
+        const uint32_t left = logS - lam0;
+        if (left >= 3 && left != 4) { ntt_round_plain<3>(sm, tw, rs, log_cj, logS, lam0); lam0 += 3; }
+        else if (left >= 2) { ntt_round_plain<2>(sm, tw, rs, log_cj, logS, lam0); lam0 += 2; }
+        else { ntt_round_plain<1>(sm, tw, rs, log_cj, logS, lam0); lam0 += 1; }
+        __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(256, 3) k_ntt_pass(const NttPass p) {
+template <int RHO, int NC>
+__device__ __forceinline__ void ntt_round(fe* sm, const fe4* tw, uint32_t rs, uint32_t log_cj, uint32_t logS, uint32_t lam0) {
+    // a thread owns columns jj and (NC == 2) jj + cj/2 of one unit
+    const uint32_t log_cw = log_cj - (NC == 2 ? 1u : 0u);
+    const uint32_t cw_mask = (1u << log_cw) - 1u;
+    const uint32_t units = (1u << (logS - RHO)) << log_cw;
+    for (uint32_t idx = threadIdx.x; idx < units; idx += blockDim.x) {
+        const uint32_t jj = idx & cw_mask, u = idx >> log_cw;
+        const uint32_t base = (u & ((1u << lam0) - 1u)) + ((u >> lam0) << (lam0 + RHO));
+        ntt_unit<RHO, NC>(sm + jj, rs, 1u << log_cw, tw, base, lam0);
+    }
+}
+template <int NC>
+__device__ __forceinline__ void ntt_rounds(fe* sm, const fe4* tw, uint32_t rs, uint32_t log_cj, uint32_t logS) {
+    // rounds of up to three layers held in registers
+    for (uint32_t lam0 = 0; lam0 < logS;) {
+        const uint32_t left = logS - lam0;
+        if (left >= 3 && left != 4) { ntt_round<3, NC>(sm, tw, rs, log_cj, logS, lam0); lam0 += 3; }
+        else if (left >= 2) { ntt_round<2, NC>(sm, tw, rs, log_cj, logS, lam0); lam0 += 2; }
+        else { ntt_round<1, NC>(sm, tw, rs, log_cj, logS, lam0); lam0 += 1; }
+        __syncthreads();
+    }
+}
+
+// PRE = true (tiles of >= 4 columns): four-copy twiddles; two blocks of 256 threads per SM, a thread carries a two-column radix-8
+// unit (16 elements + one fe4 twiddle in registers, ILP 8), and a 256-row x 16-column tile plus its 255 four-copy twiddles is
+// 86 KB of shared memory.  PRE = false (1-2 columns): plain twiddles, one column per thread, three blocks per SM when they fit.
+template <bool PRE>
+__global__ void __launch_bounds__(256, PRE ? 2 : 3) k_ntt_pass(const NttPass p) {
     extern __shared__ uint4 smem_raw[];
     fe* sm = reinterpret_cast<fe*>(smem_raw);
     const uint32_t logS = p.b - p.a, S = 1u << logS, cj = p.cj;
     const uint32_t log_cj = 31 - __clz(cj);
     const uint32_t rs = cj + (cj > 1 ? 1u : 0u);  // padded row stride: conflict-free column reads
-    fe* tw = sm + (size_t)S * rs;
+    fe4* tw = reinterpret_cast<fe4*>(sm + (size_t)S * rs);
+    fe* tw1 = sm + (size_t)S * rs;
 
     // tile coordinates: column tile fastest, then coset (so one input tile is reused out of L2), then (t_low, u0)
     const uint32_t n_ct = (p.ncols + cj - 1) >> log_cj;
@@ -206,12 +283,16 @@ __global__ void __launch_bounds__(256, 3) k_ntt_pass(const NttPass p) {
     const uint32_t k = p.coset0 + kk;
     const fe* in = p.in + (size_t)kk * p.in_coset_stride;
     fe* out = p.out + (size_t)kk * p.out_coset_stride;
-    // twiddles: tw[2^(lam-1) - 1 + th] = s_l * w_{2^l}^{t_low} * w_{2^lam}^{th},  l = a + lam
+    // twiddles: tw[2^(lam-1) - 1 + th] = s_l * w_{2^l}^{t_low} * w_{2^lam}^{th},  l = a + lam; the three shifted copies are
+    // derived here (three shift-folds per twiddle, once per tile)
     if (p.tw_tab) {
         const fe* t = p.tw_tab + ((size_t)(k << p.a) + t_low) * (S - 1u);
-        for (uint32_t q = threadIdx.x; q + 1 < S; q += blockDim.x) tw[q] = fe_ldg(t + q);
+        for (uint32_t q = threadIdx.x; q + 1 < S; q += blockDim.x) { if (PRE) tw[q] = fe4_from(fe_ldg(t + q)); else tw1[q] = fe_ldg(t + q); }
     } else {
-        for (uint32_t q = threadIdx.x; q + 1 < S; q += blockDim.x) tw[q] = ntt_twiddle(p, k, t_low, q);
+        for (uint32_t q = threadIdx.x; q + 1 < S; q += blockDim.x) {
+            const fe w = ntt_twiddle(p, k, t_low, q);
+            if (PRE) tw[q] = fe4_from(w); else tw1[q] = w;
+        }
     }
     // load: row v of the tile is input row (u0 + (n/2^b) v) * 2^a + t_low; store bit-reversed.
     // blockDim (256) is a multiple of cj, so a thread keeps its column and walks rows with a constant pointer stride.
@@ -231,14 +312,9 @@ __global__ void __launch_bounds__(256, 3) k_ntt_pass(const NttPass p) {
         }
     }
     __syncthreads();
-    // butterflies: rounds of up to three layers held in registers
-    for (uint32_t lam0 = 0; lam0 < logS;) {
-        const uint32_t left = logS - lam0;
-        if (left >= 3 && left != 4) { ntt_round<3>(sm, tw, rs, log_cj, logS, lam0); lam0 += 3; }
-        else if (left >= 2) { ntt_round<2>(sm, tw, rs, log_cj, logS, lam0); lam0 += 2; }
-        else { ntt_round<1>(sm, tw, rs, log_cj, logS, lam0); lam0 += 1; }
-        __syncthreads();
-    }
+    // butterflies
+    if (PRE) ntt_rounds<2>(sm, tw, rs, log_cj, logS);
+    else ntt_rounds_plain(sm, tw1, rs, log_cj, logS);
     // store
     if (p.out_panel) {
         // panel = k*2^a + t_low, slot = t_high; consecutive threads write consecutive slots of one column.  A thread keeps its

@@ -176,7 +176,8 @@ struct zkb_ctx {
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
         sm_count = prop.multiProcessorCount;
-        CK(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         for (auto& pr : tev) for (auto& x : pr) CK(cudaEventCreate(&x));
         h_stage_cap = (size_t)8 << 20;
         CK(cudaHostAlloc((void**)&h_stage, h_stage_cap, cudaHostAllocDefault));
@@ -282,8 +283,12 @@ struct zkb_ctx {
     // 16-column tiles (256 rows, 3 blocks/SM) were measured against 8-column tiles at 4 blocks/SM (64 registers): no gain,
     // the pass kernel is bound by integer issue, not occupancy
     static uint32_t pick_cj(uint32_t ncols) { return ncols >= 9 ? 16 : ncols >= 5 ? 8 : ncols >= 3 ? 4 : ncols == 2 ? 2 : 1; }
+    // tiles of >= 4 columns keep four pre-shifted copies of every twiddle (k_ntt_pass<true>)
+    static bool pre_twiddles(uint32_t cj) { return cj >= 4; }
     static std::vector<uint32_t> plan_layers(uint32_t log_len, uint32_t cj) {
-        uint32_t maxlog = 12 - log2u(cj);  // S * cj <= 4096 elements in shared memory
+        // plain twiddles: S * cj <= 4096 elements in shared memory; four-copy twiddles: tile + 4 S twiddles <= ~107 KB so that two
+        // blocks share an SM (256 x 16, 512 x 8, 512 x 4)
+        uint32_t maxlog = pre_twiddles(cj) ? (cj >= 16 ? 8 : 9) : 12 - log2u(cj);
         uint32_t passes = (log_len + maxlog - 1) / maxlog;
         if (passes == 0) passes = 1;
         std::vector<uint32_t> b;  // cumulative layer boundaries
@@ -320,10 +325,17 @@ struct zkb_ctx {
     void launch_pass(NttPass& p) {
         const uint32_t S = 1u << (p.b - p.a);
         const uint32_t rs = p.cj + (p.cj > 1 ? 1 : 0);
-        const size_t smem = ((size_t)S * rs + S) * 16;
+        const bool pre = pre_twiddles(p.cj);
+        const size_t smem = ((size_t)S * rs + (pre ? 4 : 1) * (size_t)S) * 16;   // tile + twiddles (four copies each for wide tiles)
         const uint64_t tiles = (uint64_t)((p.ncols + p.cj - 1) / p.cj) * p.n_cosets * ((uint64_t)1 << (p.log_n - (p.b - p.a)));
         if (tiles > 0x7fffffffull) throw InvalidArg("transform too large for one launch");
-        k_ntt_pass<<<(unsigned)tiles, 256, smem, stream>>>(p);
+        if (pre) {
+            // one two-column radix-8 unit per thread and round: S * cj / 16 threads keep every thread busy (128-row tiles of the
+            // three-pass transforms get 128-thread blocks, four per SM); never fewer than the panel store needs (min(S, 256))
+            uint32_t threads = std::max<uint32_t>(S * p.cj / 16, std::min<uint32_t>(S, 256));
+            threads = std::min<uint32_t>(256, std::max<uint32_t>(32, threads));
+            k_ntt_pass<true><<<(unsigned)tiles, threads, smem, stream>>>(p);
+        } else k_ntt_pass<false><<<(unsigned)tiles, 256, smem, stream>>>(p);
         check_launch();
     }
     // generic multi-pass transform of `ncols` columns of length 2^log_len.
