@@ -495,10 +495,10 @@ def main():
     launches_per_proof = (ctx.launches() - l0) // args.steps
     ms_latency = g0.elapsed_time(g1)
     # ---- device-resident throughput arm (`value`): `inflight` proofs per GPU per step ------------------------------------------------
-    run_lanes(dev_fn, args.warmup)
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
+    run_lanes(dev_fn, args.warmup)   # after the sampler's start-up pause: the timed region begins with clocks and lanes warm
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()

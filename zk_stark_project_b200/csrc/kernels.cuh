@@ -458,17 +458,14 @@ struct EvalParams {
     const fe* tcoef;              // transition coefficients (alpha^0 ..)
     uint32_t n_groups;
     uint32_t g_off[ZKB_MAX_GROUPS + 1];  // assertion ranges per boundary group
-    fe g_point[ZKB_MAX_GROUPS];   // g^step of the group's divisor (x - g^step)
     const uint32_t* a_col;        // per assertion of this column window: column, index into the global (sorted) assertion list
     const uint32_t* a_sel;
     const fe* a_val;              // global assertion values / coefficients (device-resident: written per proof, read by index)
     const fe* a_coef;
-    const fe* zinv;               // 1/(x^n - 1) for the 2^log_ce cosets used
-    fe g_last;                    // g^(n-1): transition exemption point
+    const fe* div;                // divisor table of the shape, [(n_groups + 1)][ce n] (k_build_divisors)
     const fe* params;             // aggregation: params[0] = scaling factor k (src/aggregation/air.rs:108)
     const fe* periodic;           // MiMC: round-constant column over the ce domain, length per_len
     uint32_t per_mask;
-    PowTab roots; uint32_t log_tab;
     fe* out;                      // composition trace, natural ce-domain order
     // boundary numerators as polynomials: bnd column g holds B_g(x) = sum_a coef_a (T_col_a(x) - value_a) over the ce domain
     // (combined in coefficient space by k_boundary_combine, extended once); used when that is cheaper than per-point sums
@@ -507,99 +504,113 @@ __global__ void __launch_bounds__(256) k_boundary_combine(const fe* __restrict__
     }
 }
 
-// Each thread evaluates RPT points and shares ONE field inversion (Montgomery batch trick) between all their
-// boundary-divisor denominators: an inversion is ~250 multiplications, as much as the rest of a row's work.
-// RPT is picked by the host: 8 for large domains, 1 when the domain is too small to fill the GPU otherwise.
-template <int ZKB_EVAL_RPT>
-__global__ void __launch_bounds__(128) k_eval_constraints(const EvalParams p) {
-    const LdeMat& m = p.lde;
-    const uint64_t total = (uint64_t)1 << (m.log_n + p.log_ce);
-    const uint64_t nthreads = total / ZKB_EVAL_RPT;
+// Divisor table of a shape: everything in the combination that depends only on the evaluation point x = 3 * w_{ce n}^ci —
+//   div[g][ci]  = 1 / (x - g^step_g)                    boundary divisors (Air::get_assertions groups)
+//   div[ng][ci] = (x - g^(n-1)) / (x^n - 1)             inverse of the transition divisor (x^n - 1)/(x - g^(n-1))
+// It does not depend on the trace or on any challenge, so it is built once per (n, ce, assertion steps) and cached by the
+// context: the ~45 multiplications per point that the batch inversions cost are paid by the first proof of a shape only.
+struct DivParams {
+    uint32_t log_cen, log_ce, n_groups;
+    fe g_point[ZKB_MAX_GROUPS];
+    fe g_last;
+    const fe* zinv;               // 1/(x^n - 1) for the 2^log_ce cosets of the ce domain
+    PowTab roots; uint32_t log_tab;
+    fe* out;                      // [(n_groups + 1)][2^log_cen]
+};
+#define ZKB_DIV_RPT 8
+__global__ void __launch_bounds__(128) k_build_divisors(const DivParams p) {
+    const uint64_t total = (uint64_t)1 << p.log_cen;
+    const uint64_t nthreads = total / ZKB_DIV_RPT;    // ce * n >= 16: a multiple of 8
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= nthreads) return;
-    const uint32_t lpf = lde_full_log_p(m), lt = m.log_n - lpf;
-    const uint32_t log_N = m.log_n + m.log_beta;
-    const size_t cs = (size_t)1 << m.log_p;  // column stride
     const uint32_t ng = p.n_groups;
-
-    fe num[ZKB_EVAL_RPT * ZKB_MAX_GROUPS], den[ZKB_EVAL_RPT * ZKB_MAX_GROUPS], pre[ZKB_EVAL_RPT * ZKB_MAX_GROUPS];
-    fe tpart[ZKB_EVAL_RPT];
-    uint32_t cidx[ZKB_EVAL_RPT];
+    fe den[ZKB_DIV_RPT * ZKB_MAX_GROUPS], pre[ZKB_DIV_RPT * ZKB_MAX_GROUPS];
     fe acc = fe_one();
-    for (int s = 0; s < ZKB_EVAL_RPT; s++) {
-        const uint64_t gid = tid + (uint64_t)s * nthreads;
-        const uint32_t slot = (uint32_t)gid & ((1u << lpf) - 1u);
-        const uint32_t t_low = (uint32_t)(gid >> lpf) & ((1u << lt) - 1u);
-        const uint32_t kc = (uint32_t)(gid >> m.log_n);
-        const uint32_t k = kc << (m.log_beta - p.log_ce);
-        const uint32_t i = t_low + (slot << lt);
-        const uint32_t i1 = (i + 1u) & ((1u << m.log_n) - 1u);  // frame.next = row + blowup (mod N)
-        const uint32_t ci = (i << p.log_ce) + kc;
-        const uint32_t r = (i << m.log_beta) + k;
-        cidx[s] = ci;
-        const fe* cur = m.data + lde_row_base(m, k, i);   // send view / single GPU: columns are local, stride 2^log_p
-        const fe* nxt = m.data + lde_row_base(m, k, i1);
-
-        // x = 3 * w_N^r
-        fe x = powtab(p.roots, r << (p.log_tab - log_N));
-        { fe x2 = fe_add(x, x); x = fe_add(x2, x); }
-
-        // transition constraints, merged with their coefficients.  sum_c coef_c * ev_c is accumulated as an exact 288-bit
-        // integer and reduced once per point (acc288): same field element, one reduction instead of one per column
-        acc288 tacc; acc288_zero(tacc);
-        if (p.air_id == ZKB_AIR_AGGREGATION) {
-            const uint32_t d = p.n_trans;
-            const fe kf = fe_ldg(p.params);
-            for (uint32_t c = 0; c < d; c++) {
-                fe dn = fe_sub(fe_load(nxt + c * cs), fe_load(cur + c * cs));
-                fe ev = fe_sub(fe_mul(kf, dn), fe_load(nxt + (size_t)(c + d) * cs));
-                acc288_mad(tacc, fe_ldg(p.tcoef + c), ev);
-            }
-        } else if (p.air_id == ZKB_AIR_MIMC) {
-            const fe rc = fe_ldg(p.periodic + (ci & p.per_mask));
-            for (uint32_t c = 0; c < p.n_trans; c++) {
-                fe a1 = fe_add(fe_load(cur + c * cs), rc);
-                fe a2 = fe_sqr(a1), a4 = fe_sqr(a2), a6 = fe_mul(a4, a2), a7 = fe_mul(a6, a1);
-                fe ev = fe_sub(fe_load(nxt + c * cs), a7);
-                acc288_mad(tacc, fe_ldg(p.tcoef + c), ev);
-            }
-        }  // TRAINING: every transition evaluation is zero (src/training/air.rs:274-278, src/helper.rs:141-146)
-        const fe t = acc288_reduce(tacc);
-        tpart[s] = fe_mul(fe_mul(t, fe_sub(x, p.g_last)), fe_ldg(p.zinv + kc));
-
-        // boundary groups: sum coef * (cur[col] - value), to be divided by (x - g^step)
-        const fe* bp = p.bnd_poly ? p.bnd.data + lde_row_base(p.bnd, kc, i) : nullptr;
+    for (int s = 0; s < ZKB_DIV_RPT; s++) {
+        const uint32_t ci = (uint32_t)(tid + (uint64_t)s * nthreads);
+        fe x = powtab(p.roots, ci << (p.log_tab - p.log_cen));
+        { fe x2 = fe_add(x, x); x = fe_add(x2, x); }     // x = 3 * w^ci
+        fe_store(p.out + ((size_t)ng << p.log_cen) + ci, fe_mul(fe_sub(x, p.g_last), fe_ldg(p.zinv + (ci & ((1u << p.log_ce) - 1u)))));
         for (uint32_t g = 0; g < ng; g++) {
-            fe sum = fe_zero();
-            if (p.bnd_poly) {
-                sum = fe_load(bp + ((size_t)g << p.bnd.log_p));
-            } else {
-                acc288 bacc; acc288_zero(bacc);
-                for (uint32_t a = p.g_off[g]; a < p.g_off[g + 1]; a++) {
-                    const uint32_t ai = __ldg(p.a_sel + a);
-                    fe v = fe_sub(fe_load(cur + (size_t)__ldg(p.a_col + a) * cs), fe_ldg(p.a_val + ai));
-                    acc288_mad(bacc, fe_ldg(p.a_coef + ai), v);
-                }
-                sum = acc288_reduce(bacc);
-            }
             const uint32_t q = s * ZKB_MAX_GROUPS + g;
-            num[q] = sum;
             den[q] = fe_sub(x, p.g_point[g]);
             pre[q] = acc;
             acc = fe_mul(acc, den[q]);
         }
     }
-    fe ia = ng ? fe_inv(acc) : fe_one();
-    for (int s = ZKB_EVAL_RPT - 1; s >= 0; s--) {
-        fe res = tpart[s];
+    fe ia = ng ? fe_inv(acc) : fe_one();     // one inversion shared by 8 points (Montgomery's trick)
+    for (int s = ZKB_DIV_RPT - 1; s >= 0; s--) {
+        const uint32_t ci = (uint32_t)(tid + (uint64_t)s * nthreads);
         for (int g = (int)ng - 1; g >= 0; g--) {
             const uint32_t q = s * ZKB_MAX_GROUPS + g;
-            fe di = fe_mul(ia, pre[q]);
+            fe_store(p.out + ((size_t)g << p.log_cen) + ci, fe_mul(ia, pre[q]));
             ia = fe_mul(ia, den[q]);
-            res = fe_add(res, fe_mul(num[q], di));
         }
-        fe_store(p.out + cidx[s], res);
     }
+}
+
+// One thread per constraint-evaluation-domain point:  sum_c coef_c * transition_c(frame) * div[ng]  +  sum_g numerator_g * div[g]
+__global__ void __launch_bounds__(128) k_eval_constraints(const EvalParams p) {
+    const LdeMat& m = p.lde;
+    const uint64_t total = (uint64_t)1 << (m.log_n + p.log_ce);
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const uint32_t lpf = lde_full_log_p(m), lt = m.log_n - lpf;
+    const size_t cs = (size_t)1 << m.log_p;  // column stride
+    const uint32_t ng = p.n_groups;
+    // enumerate points (coset, panel, slot) so that a warp reads 32 consecutive slots of every column
+    const uint32_t slot = (uint32_t)gid & ((1u << lpf) - 1u);
+    const uint32_t t_low = (uint32_t)(gid >> lpf) & ((1u << lt) - 1u);
+    const uint32_t kc = (uint32_t)(gid >> m.log_n);
+    const uint32_t k = kc << (m.log_beta - p.log_ce);
+    const uint32_t i = t_low + (slot << lt);
+    const uint32_t i1 = (i + 1u) & ((1u << m.log_n) - 1u);  // frame.next = row + blowup (mod N)
+    const uint32_t ci = (i << p.log_ce) + kc;
+    const uint32_t log_cen = m.log_n + p.log_ce;
+    const fe* cur = m.data + lde_row_base(m, k, i);   // send view / single GPU: columns are local, stride 2^log_p
+    const fe* nxt = m.data + lde_row_base(m, k, i1);
+
+    // transition constraints, merged with their coefficients.  sum_c coef_c * ev_c is accumulated as an exact 288-bit
+    // integer and reduced once per point (acc288): same field element, one reduction instead of one per column
+    acc288 tacc; acc288_zero(tacc);
+    if (p.air_id == ZKB_AIR_AGGREGATION) {
+        const uint32_t d = p.n_trans;
+        const fe kf = fe_ldg(p.params);
+        for (uint32_t c = 0; c < d; c++) {
+            fe dn = fe_sub(fe_load(nxt + c * cs), fe_load(cur + c * cs));
+            fe ev = fe_sub(fe_mul(kf, dn), fe_load(nxt + (size_t)(c + d) * cs));
+            acc288_mad(tacc, fe_ldg(p.tcoef + c), ev);
+        }
+    } else if (p.air_id == ZKB_AIR_MIMC) {
+        const fe rc = fe_ldg(p.periodic + (ci & p.per_mask));
+        for (uint32_t c = 0; c < p.n_trans; c++) {
+            fe a1 = fe_add(fe_load(cur + c * cs), rc);
+            fe a2 = fe_sqr(a1), a4 = fe_sqr(a2), a6 = fe_mul(a4, a2), a7 = fe_mul(a6, a1);
+            fe ev = fe_sub(fe_load(nxt + c * cs), a7);
+            acc288_mad(tacc, fe_ldg(p.tcoef + c), ev);
+        }
+    }  // TRAINING: every transition evaluation is zero (src/training/air.rs:274-278, src/helper.rs:141-146)
+    fe res = fe_zero();
+    if (p.air_id != ZKB_AIR_TRAINING) res = fe_mul(acc288_reduce(tacc), fe_ldg(p.div + ((size_t)ng << log_cen) + ci));
+
+    // boundary groups: sum coef * (cur[col] - value) / (x - g^step)
+    const fe* bp = p.bnd_poly ? p.bnd.data + lde_row_base(p.bnd, kc, i) : nullptr;
+    for (uint32_t g = 0; g < ng; g++) {
+        fe sum;
+        if (p.bnd_poly) {
+            sum = fe_load(bp + ((size_t)g << p.bnd.log_p));
+        } else {
+            acc288 bacc; acc288_zero(bacc);
+            for (uint32_t a = p.g_off[g]; a < p.g_off[g + 1]; a++) {
+                const uint32_t ai = __ldg(p.a_sel + a);
+                fe v = fe_sub(fe_load(cur + (size_t)__ldg(p.a_col + a) * cs), fe_ldg(p.a_val + ai));
+                acc288_mad(bacc, fe_ldg(p.a_coef + ai), v);
+            }
+            sum = acc288_reduce(bacc);
+        }
+        res = fe_add(res, fe_mul(sum, fe_ldg(p.div + ((size_t)g << log_cen) + ci)));
+    }
+    fe_store(p.out + ci, res);
 }
 
 // ------------------------------------------------------------------------------------------------

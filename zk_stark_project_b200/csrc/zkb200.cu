@@ -128,6 +128,8 @@ struct zkb_ctx {
     struct FsTree { size_t o_rows, o_paths; uint32_t width, depth; };
     struct FsLayout { size_t o_ood = 0, o_rem = 0, host_bytes = 0, o_coef = 0, o_gamma = 0, o_scr = 0, total = 0; uint32_t rem_cap = 0; std::vector<FsTree> trees; } fs;
     DevBuf d_fs, d_in, d_rem_coef;      // d_in: per-proof inputs [assertion values na][AIR params]
+    DevBuf d_div;                       // divisor table of the current shape (k_build_divisors) and the shape it belongs to
+    std::vector<uint64_t> div_key;
     uint8_t* h_out = nullptr;           // pinned landing area of the final download
     size_t h_out_cap = 0;
     cudaEvent_t ev_done = nullptr;      // blocking-sync event: the host thread sleeps instead of spinning while the device works
@@ -197,7 +199,7 @@ struct zkb_ctx {
         cudaStreamSynchronize(stream);
         for (DevBuf* b : {&d_trace, &d_bufA, &d_bufB, &d_tmp1, &d_tmp2, &d_lde, &d_tree, &d_small, &d_comp_evals, &d_comp_lde, &d_comp_tree,
                           &d_ab, &d_ab_lde, &d_deep, &d_roots_lo, &d_roots_hi, &d_inv3_lo, &d_inv3_hi, &d_pow3, &d_aux, &d_gather, &d_user_trace, &d_flags,
-                          &d_lde_rows, &d_mg_a, &d_mg_b, &d_bnd_coef, &d_bnd_lde, &d_fs, &d_in, &d_rem_coef})
+                          &d_lde_rows, &d_mg_a, &d_mg_b, &d_bnd_coef, &d_bnd_lde, &d_fs, &d_in, &d_rem_coef, &d_div})
             b->release();
         if (comm) { g_nccl.CommDestroy(comm); comm = nullptr; }
         for (auto& b : d_fri_evals) b.release();
@@ -630,7 +632,7 @@ struct zkb_ctx {
         d_lde_rows.ensure(N * wl * 16);
         const size_t chunk = (size_t)(N / G) * wl * 16;  // bytes per (source, destination) pair
         const size_t per_coset = chunk >> log_beta;
-        uint32_t n_batches = std::min<uint32_t>(air.blowup, 4);
+        uint32_t n_batches = std::min<uint32_t>(air.blowup, 8);   // only the last batch's transfer is exposed
         while (n_batches > 1 && (uint64_t)n * wl * (air.blowup / n_batches) < ((uint64_t)1 << 20)) n_batches >>= 1;  // keep launches wide
         xl.batch_cosets = (uint32_t)air.blowup / n_batches;
         uint32_t shipped = 0;
@@ -759,20 +761,27 @@ struct zkb_ctx {
         p.n_trans = windowed ? ncols : nt;
         const HF g = HF::root_of_unity(log_n);
         std::vector<uint32_t> acol, asel;
+        std::vector<uint64_t> gsteps;
         uint32_t ng = 0;
         for (uint32_t i = 0; i < na; i++) {
             if (i == 0 || air.assertions[i].step != air.assertions[i - 1].step) {
-                p.g_off[ng] = (uint32_t)acol.size(); p.g_point[ng] = to_fe(g.pow(air.assertions[i].step)); ng++;
+                p.g_off[ng] = (uint32_t)acol.size(); gsteps.push_back(air.assertions[i].step); ng++;
             }
             const uint32_t col = air.assertions[i].col;
             if (col >= col0 && col < col0 + ncols) { acol.push_back(col - col0); asel.push_back(i); }
         }
         const uint32_t nl = (uint32_t)acol.size();
         p.g_off[ng] = nl; p.n_groups = ng;
-        // 1/(x^n - 1) on the cosets used by the ce domain: x^n = 3^n * w_beta^k, k = kc * beta/ce
+        // divisor table of the shape (k_build_divisors): cached until the trace length, the ce blowup or the assertion steps change
+        std::vector<uint64_t> dkey{n, ce};
+        dkey.insert(dkey.end(), gsteps.begin(), gsteps.end());
+        const bool build_div = dkey != div_key;
+        // 1/(x^n - 1) on the cosets used by the ce domain: x^n = 3^n * w_beta^k, k = kc * beta/ce   (input of the table build only)
         std::vector<HF> zinv(ce);
-        { HF on = HF::from_u64(3).pow((u128)n), wb = HF::root_of_unity(log_beta);
-          for (uint64_t kc = 0; kc < ce; kc++) zinv[kc] = (on * wb.pow((u128)(kc << (log_beta - log_ce))) - HF::raw(1)).inv(); }
+        if (build_div) {
+            HF on = HF::from_u64(3).pow((u128)n), wb = HF::root_of_unity(log_beta);
+            for (uint64_t kc = 0; kc < ce; kc++) zinv[kc] = (on * wb.pow((u128)(kc << (log_beta - log_ce))) - HF::raw(1)).inv();
+        }
         // periodic column over the ce domain (PeriodicValueTable): P_L(x^(n/L)) tabulated on 3^(n/L) * <w_{L*ce}>
         if (air.id == ZKB_AIR_ID_MIMC && !(per_cache_n == n && per_cache_ce == ce && per_cache_params.size() == air.params.size() &&
                                            std::equal(per_cache_params.begin(), per_cache_params.end(), air.params.begin()))) {
@@ -796,12 +805,27 @@ struct zkb_ctx {
         uint8_t* base = d_aux.as<uint8_t>();
         const fe* coef = fs_fe(fs.o_coef);
         p.tcoef = coef + (windowed ? col0 : 0); p.a_coef = coef + nt; p.a_val = d_aval(); p.params = d_params();
-        p.zinv = (const fe*)(base + off_z); p.periodic = (const fe*)(base + off_p);
+        p.periodic = (const fe*)(base + off_p);
         p.a_col = (const uint32_t*)(base + off_col); p.a_sel = (const uint32_t*)(base + off_sel);
         p.per_mask = per.empty() ? 0 : (uint32_t)per.size() - 1;
-        p.g_last = to_fe(g.pow((u128)(n - 1)));
-        p.roots = roots; p.log_tab = log_tab;
         p.out = out;
+        {
+            if (build_div) {
+                d_div.ensure((size_t)(ng + 1) * n * ce * 16);
+                DivParams dp{};
+                dp.log_cen = log_n + log_ce; dp.log_ce = log_ce; dp.n_groups = ng;
+                for (uint32_t gi = 0; gi < ng; gi++) dp.g_point[gi] = to_fe(g.pow((u128)gsteps[gi]));
+                dp.g_last = to_fe(g.pow((u128)(n - 1)));
+                dp.zinv = (const fe*)(base + off_z);
+                dp.roots = roots; dp.log_tab = log_tab;
+                dp.out = d_div.as<fe>();
+                const uint64_t threads = (n * ce) / ZKB_DIV_RPT;
+                k_build_divisors<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(dp);
+                check_launch();
+                div_key = dkey;
+            }
+            p.div = d_div.as<fe>();
+        }
         // Boundary numerators.  Per-point sums cost nl multiplications at each of the ce*n points; combining the asserted
         // columns in coefficient space (nl per coefficient row) and extending the ng combined polynomials once costs
         // nl*n + ng * ce*n * (log2(n)/2 + ~6).  MiMC on one GPU (128 assertions, ce = 8) is 2.7x cheaper that way; the training
@@ -826,11 +850,8 @@ struct zkb_ctx {
                 p.bnd = LdeMat{d_bnd_lde.as<fe>(), log_n, log_ce, ng, lp, 0, ng, magic16(ng), 0, 0, 0, 0, log_ce};
             }
         }
-        // rows per thread: share one inversion between 8 points once there are enough points to fill the GPU anyway
-        const uint64_t points = n * ce;  // n >= 8 and ce >= 2: always a multiple of 8
-        if (points >= ((uint64_t)1 << 21)) k_eval_constraints<8><<<(unsigned)((points / 8 + 127) / 128), 128, 0, stream>>>(p);
-        else if (points >= ((uint64_t)1 << 19)) k_eval_constraints<2><<<(unsigned)((points / 2 + 127) / 128), 128, 0, stream>>>(p);
-        else k_eval_constraints<1><<<(unsigned)((points + 127) / 128), 128, 0, stream>>>(p);
+        const uint64_t points = n * ce;
+        k_eval_constraints<<<(unsigned)((points + 127) / 128), 128, 0, stream>>>(p);
         check_launch();
     }
     // the coefficient powers must be in place (fs_after_trace_root)
