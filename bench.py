@@ -277,7 +277,8 @@ def run_mimc_helpers(args):
 # from an `ncu --set full` capture of that workload; None = not captured (never extrapolated).  Two passes through HBM per
 # 2^16-point transform (a shared-memory tile holds 2^8 rows x 16 columns) make this 2.8x the algorithmic bytes.
 NCU_TRAFFIC = {
-    "training_2p16": (13.580e9, "profiles/r1_ncu_k1k2_dram_traffic.csv (kernel structure unchanged in round 2: same tiles, same passes)"),
+    # interpolation passes 0.457 + 0.458 GB, LDE passes 4.259 + 8.031 GB (k_ntt_pass<true> x 4; the 0.5 GB transpose is not included)
+    "training_2p16": (13.204e9, "profiles/r2_ncu_ntt_hash_training_2p16.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the four K1+K2 launches)"),
 }
 OPTIONS_TEXT = "40 queries, grinding 21, FRI folding 16, remainder degree <= 7"
 
@@ -332,12 +333,13 @@ def roofline_of(workload, n, w_local, beta, lde_ms, alg_lde, peak, peak_src, sha
                      "frac": achieved / peak, "traffic": traffic[0] if traffic else None,
                      "traffic_source": traffic[1] if traffic else "no ncu --set full capture of this workload",
                      "peak_source": peak_src, "algorithmic_bytes_per_proof": alg_lde, "kernel_ms_per_proof": lde_ms,
-                     "note": "bound by integer issue, not HBM: a radix-2 f128 butterfly is ~87 SASS integer instructions per 32 bytes moved "
-                             "(profiles/r2_mul_variants.txt, profiles/r2_sass_hist_k_ntt_pass.txt); ncu: issue-slot utilisation ~55%, DRAM 10-20%"},
-        # what actually bounds K1/K2: integer issue.  Peak = register-resident radix-2 f128 butterflies/s of the shipped multiplier on this
-        # pool's B200 (tools/mul_variants.cu variant E; no memory traffic at all)
-        "compute_roofline": {"unit": "G butterflies/s", "peak": 237.2, "achieved": bf / (lde_ms * 1e-3) / 1e9,
-                             "frac": bf / (lde_ms * 1e-3) / 1e9 / 237.2, "source": "tools/mul_variants.cu variant E, profiles/r2_mul_variants.txt"},
+                     "note": "bound by integer issue, not HBM: a radix-2 f128 butterfly is ~69 SASS integer instructions per 32 bytes moved "
+                             "(profiles/r2_mul_variants.txt, profiles/r2_sass_hist_hot_kernels.txt); ncu (profiles/r2_ncu_ntt_hash_training_2p16.txt): "
+                             "issue slots 53-54% busy, ALU pipe 63%, FMA-heavy pipe 54%, DRAM 12-21% of peak"},
+        # what actually bounds K1/K2: integer issue.  Peak = register-resident radix-2 f128 butterflies/s of the shipped twiddle multiplier
+        # (four pre-shifted copies) on this pool's B200, best occupancy / ILP setting (tools/mul_variants.cu variant F; no memory traffic at all)
+        "compute_roofline": {"unit": "G butterflies/s", "peak": 270.5, "achieved": bf / (lde_ms * 1e-3) / 1e9,
+                             "frac": bf / (lde_ms * 1e-3) / 1e9 / 270.5, "source": "tools/mul_variants.cu variant F (251-270 G/s depending on ILP), profiles/r2_mul_variants.txt"},
     }
 
 
