@@ -343,6 +343,25 @@ def roofline_of(workload, n, w_local, beta, lde_ms, alg_lde, peak, peak_src, sha
     }
 
 
+def pin_to_gpu_numa_node(device):
+    """Multi-rank runs: bind this process (and with it the first-touch placement of its pinned trace buffers) to the CPUs NVML
+    reports as local to its GPU, so that the end-to-end arm's H2D copies do not cross the socket interconnect.  Host plumbing
+    only; returns the CPU count it was pinned to, or None when NVML / affinity is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -381,6 +400,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the zkb200 proving path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = pin_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -695,7 +715,7 @@ def main():
             "scaling": "strong" if sharded else "weak",
             "vs_baseline": None, "dtype": "u128 mod p (f128 field, 4x u32 limbs), u32 BLAKE3", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "options": OPTIONS_TEXT, "l2": l2_text(n, w, beta)},
-            "run": {"proofs_per_gpu_per_step": inflight, "proof_bytes": main_proof_len,
+            "run": {"proofs_per_gpu_per_step": inflight, "proof_bytes": main_proof_len, "host_cpus_per_rank": numa or (os.cpu_count() or 1),
                     "parallelism": (f"one proof column-sharded over {world} GPUs: NCCL all-to-all (NVLink transpose) + all-gathers" if sharded
                                     else f"{world} independent proof stream(s), one per GPU, no data-path collective")},
             "prove_ms": ms_latency / args.steps,
