@@ -173,3 +173,34 @@ def test_chacha20_block_known_answer():
     assert ks.hex() == ("76b8e0ada0f13d90405d6ae55386bd28bdd219b8a08ded1aa836efcc8b770dc7"
                         "da41597c5157488d7724e03fb8d84a376a43b8f41518a11cc387b669b2ee6586")
     assert T.chacha20_block(bytes(32), 1).hex().startswith("9f07e7be5551387a98ba977c732d080d")
+
+
+def test_bench_counter_trace_is_seekable_and_canonical():
+    """bench.py's counter-based synthetic trace: a rank that builds only its columns gets exactly the slice of the full trace
+    (the sharded arm relies on it), every cell is a canonical field element, and the AIR description built from the two boundary
+    rows equals the one built from the whole trace."""
+    import numpy as np
+    import bench
+    import zk_stark_project_b200 as Z
+    from zk_stark_project_b200 import synthetic as S
+    w, n = 12, 64
+    full = bench.counter_felts(w, n, 0x5EED2000)
+    assert full.shape == (w, n, 2) and np.all(full[:, :, 1] < np.uint64(1 << 63))
+    for r, world in ((0, 4), (3, 4), (1, 2)):
+        wl = w // world
+        assert np.array_equal(bench.counter_felts(w, n, 0x5EED2000, r * wl, wl), full[r * wl:(r + 1) * wl])
+    assert not np.array_equal(bench.counter_felts(w, n, 1), full)
+    opts = Z.ProofOptions(40, 16, 21, Z.FieldExtension.NONE, 16, 7)
+    get = lambda c, r: int(full[c, r, 0]) | (int(full[c, r, 1]) << 64)
+    a = bench.training_air_from_rows(n, w, opts, [get(j, 0) for j in range(w)], [get(j, n - 1) for j in range(w)])
+    b = S.synthetic_training_air(n, opts, full)
+    assert a == b
+
+
+def test_bench_algorithmic_bytes_match_survey():
+    """SURVEY §8(d) totals: 9.47 GiB at configs[1], 33.5 GiB / 151.6 GiB at the two 2^20-row headline shapes."""
+    import bench
+    gib = 1 << 30
+    assert abs(bench.algorithmic_bytes(1 << 16, 240, 16, 2, 1)["total"] / gib - 9.47) < 0.02
+    assert abs(bench.algorithmic_bytes(1 << 20, 64, 8, 8, 6)["total"] / gib - 33.5) < 0.1
+    assert abs(bench.algorithmic_bytes(1 << 20, 240, 16, 2, 1)["total"] / gib - 151.6) < 0.2
