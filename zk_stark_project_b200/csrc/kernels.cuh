@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(256, PRE ? 2 : 3) k_ntt_pass(const NttPass p) 
     }
     __syncthreads();
     // butterflies
-    if (PRE) ntt_rounds<2>(sm, tw, rs, log_cj, logS);
+    if (PRE) { if (cj >= 16) ntt_rounds<2>(sm, tw, rs, log_cj, logS); else ntt_rounds<1>(sm, tw, rs, log_cj, logS); }   // narrow tiles: one column per thread
     else ntt_rounds_plain(sm, tw1, rs, log_cj, logS);
     // store
     if (p.out_panel) {

@@ -334,7 +334,8 @@ struct zkb_ctx {
         if (pre) {
             // one two-column radix-8 unit per thread and round: S * cj / 16 threads keep every thread busy (128-row tiles of the
             // three-pass transforms get 128-thread blocks, four per SM); never fewer than the panel store needs (min(S, 256))
-            uint32_t threads = std::max<uint32_t>(S * p.cj / 16, std::min<uint32_t>(S, 256));
+            const uint32_t units = p.cj >= 16 ? S * p.cj / 16 : S * p.cj / 8;   // radix-8 units per round (two columns each for 16-wide tiles)
+            uint32_t threads = std::max<uint32_t>(units, std::min<uint32_t>(S, 256));
             threads = std::min<uint32_t>(256, std::max<uint32_t>(32, threads));
             k_ntt_pass<true><<<(unsigned)tiles, threads, smem, stream>>>(p);
         } else k_ntt_pass<false><<<(unsigned)tiles, 256, smem, stream>>>(p);
@@ -854,6 +855,25 @@ struct zkb_ctx {
         k_eval_constraints<<<(unsigned)((points + 127) / 128), 128, 0, stream>>>(p);
         check_launch();
     }
+    // out[i] = sum over ranks of partial[i] (mod p), on every rank.  NCCL cannot add 128-bit field elements, so the reduction is
+    // a hand-written reduce-scatter — slice q of every rank's vector goes to rank q (grouped send/recv), which sums the G slices
+    // (k_sum_partials) — followed by an all-gather of the summed slices: no rank ever receives G full vectors.
+    void mg_field_allreduce(const fe* partial, uint64_t count, fe* out) {
+        const uint32_t G = (uint32_t)mg_world;
+        if (count % G) throw InvalidArg("vector length must be divisible by the number of GPUs");
+        const uint64_t sl = count / G;
+        d_mg_b.ensure(count * 16 + sl * 16);
+        NK(g_nccl.GroupStart());
+        for (uint32_t q = 0; q < G; q++) {
+            NK(g_nccl.Send(partial + q * sl, sl * 16, ncclUint8, (int)q, comm, stream));
+            NK(g_nccl.Recv(d_mg_b.as<fe>() + q * sl, sl * 16, ncclUint8, (int)q, comm, stream));
+        }
+        NK(g_nccl.GroupEnd());
+        fe* mine = d_mg_b.as<fe>() + count;
+        k_sum_partials<<<(unsigned)((sl + 255) / 256), 256, 0, stream>>>(d_mg_b.as<fe>(), G, sl, sl, mine);
+        check_launch();
+        NK(g_nccl.AllGather(mine, out, sl * 16, ncclUint8, comm, stream));
+    }
     // the coefficient powers must be in place (fs_after_trace_root)
     void constraints_eval_dev() {
         if (stage != ST_TRACE) throw StateError("zkb_constraints_eval: trace is not committed");
@@ -863,24 +883,11 @@ struct zkb_ctx {
         if (!mg_active) {
             constraints_eval_window(lde_mat(), 0, air.w, d_comp_evals.as<fe>());
         } else {
-            // column-sharded: partial evaluation over this rank's columns, all-gather, field sum
-            // reduce-scatter by hand (NCCL cannot add mod p): slice q of every rank's partial vector goes to rank q, which
-            // sums the G slices; the summed slices are all-gathered
-            const uint32_t wl = air.w / (uint32_t)mg_world, G = (uint32_t)mg_world;
-            const uint64_t total = n * ce, sl = total / G;
-            d_mg_a.ensure(total * 16);
-            d_mg_b.ensure(total * 16 + sl * 16);
+            // column-sharded: partial evaluation over this rank's columns, then a field all-reduce
+            const uint32_t wl = air.w / (uint32_t)mg_world;
+            d_mg_a.ensure(n * ce * 16);
             constraints_eval_window(lde_mat(), mg_rank * wl, wl, d_mg_a.as<fe>());
-            NK(g_nccl.GroupStart());
-            for (uint32_t q = 0; q < G; q++) {
-                NK(g_nccl.Send(d_mg_a.as<fe>() + q * sl, sl * 16, ncclUint8, (int)q, comm, stream));
-                NK(g_nccl.Recv(d_mg_b.as<fe>() + q * sl, sl * 16, ncclUint8, (int)q, comm, stream));
-            }
-            NK(g_nccl.GroupEnd());
-            fe* mine = d_mg_b.as<fe>() + total;
-            k_sum_partials<<<(unsigned)((sl + 255) / 256), 256, 0, stream>>>(d_mg_b.as<fe>(), G, sl, sl, mine);
-            check_launch();
-            NK(g_nccl.AllGather(mine, d_comp_evals.p, sl * 16, ncclUint8, comm, stream));
+            mg_field_allreduce(d_mg_a.as<fe>(), n * ce, d_comp_evals.as<fe>());
         }
         t_end(TS_CONSTR);
         stage = ST_EVAL;
@@ -1039,16 +1046,13 @@ struct zkb_ctx {
             k_deep_combine<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(d_polys, (uint32_t)n, w, gamma, d_bufA.as<fe>(), c, gamma + w, d_ab.as<fe>());
             check_launch();
         } else {
-            // partial A over this rank's columns -> all-gather -> field sum -> add the (replicated) H part
+            // partial A over this rank's columns -> field all-reduce -> add the (replicated) H part
             const uint32_t wl = w / (uint32_t)mg_world;
             d_mg_a.ensure(n * 2 * 16);
-            d_mg_b.ensure(n * 2 * 16 * mg_world);
             k_deep_combine<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(d_polys, (uint32_t)n, wl, gamma + (size_t)mg_rank * wl, d_bufA.as<fe>(), 0,
                                                                               gamma + w, d_mg_a.as<fe>());
             check_launch();
-            NK(g_nccl.AllGather(d_mg_a.p, d_mg_b.p, n * 2 * 16, ncclUint8, comm, stream));
-            k_sum_partials<<<(unsigned)((2 * n + 255) / 256), 256, 0, stream>>>(d_mg_b.as<fe>(), mg_world, 2 * n, 2 * n, d_ab.as<fe>());
-            check_launch();
+            mg_field_allreduce(d_mg_a.as<fe>(), 2 * n, d_ab.as<fe>());
             k_deep_add_h<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_ab.as<fe>(), (uint32_t)n, d_bufA.as<fe>(), c, gamma + w);
             check_launch();
         }
