@@ -102,6 +102,9 @@ void zkb_host_free(void* p);
  * cols: trace_width host pointers, column j = trace_len elements (TraceTable columns, column-major).
  * force_nonce: 0 = grind for the smallest valid nonce (non-`concurrent` Winterfell); otherwise use it.
  * proof_out: Proof::to_bytes() layout, allocated by the library; release with zkb_free.
+ * The Fiat-Shamir channel runs on the device: the call enqueues every stage without waiting, blocks once, downloads the
+ * transcript and the openings in one copy and assembles the proof.  Small proofs (LDE rows x width < 2^22) are replayed from a
+ * CUDA graph from the third proof of a shape on; coin seed, assertion values, AIR parameters and the trace are per-proof inputs.
  */
 int32_t zkb_prove(zkb_ctx* ctx, const zkb_air_desc* air, const uint8_t* const* cols, uint64_t force_nonce,
                   uint8_t** proof_out, uint64_t* proof_len, zkb_transcript* transcript);

@@ -191,3 +191,29 @@ def test_invalid_trace_reports_degree_failure(gpu_ctx, oracle):
     # and a valid trace keeps the flag set
     _, ts = gpu_ctx.prove_host(air, np.ascontiguousarray(trace.data).ctypes.data)
     assert ts.comp_degree_ok == 1
+
+
+def test_graph_replay_small_proofs(oracle):
+    """Small proofs are replayed from a CUDA graph from the third proof of a shape on (first eager, second captured): every
+    replay must honour that proof's own trace, public inputs and assertion values.  Different seeds, same shape, each proof
+    compared with the oracle; interleaved with a second shape so that both graphs stay valid side by side."""
+    ctx = L.Context(0, own_stream=True)
+    for rnd in range(5):
+        p = T.aggregation_prover(16, Z.ProofOptions.reference(), seed=0x5EED0003 + rnd)
+        tr = p.build_trace()
+        air = p.describe(tr)
+        got, ts = ctx.prove_host(air, np.ascontiguousarray(tr.data).ctypes.data)
+        ref, ts_o, _ = oracle.prove(air, tr.to_bytes())
+        assert T.transcript_diff(ts_o, ts) is None and got == ref, f"aggregation proof {rnd} differs"
+        m = Z.MimcProver(T.options(blowup=8, grinding=5), [100 * rnd + j + 1 for j in range(4)], 256)
+        mt = m.build_trace()
+        mair = m.describe(mt)
+        got, _ = ctx.prove_host(mair, np.ascontiguousarray(mt.data).ctypes.data)
+        assert got == oracle.prove(mair, mt.to_bytes())[0], f"mimc proof {rnd} differs"
+    # a forced nonce takes the eager path and must still work on the same context
+    p = T.aggregation_prover(16, T.options(grinding=0))
+    tr = p.build_trace()
+    air = p.describe(tr)
+    got, ts = ctx.prove_host(air, np.ascontiguousarray(tr.data).ctypes.data, force_nonce=12345)
+    assert ts.pow_nonce == 12345 and got == oracle.prove(air, tr.to_bytes(), force_nonce=12345)[0]
+    ctx.close()

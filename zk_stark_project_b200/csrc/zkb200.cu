@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 #include <sys/random.h>
 #include <nccl.h>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -40,17 +41,22 @@ static thread_local std::string g_last_error;
 #include "nccl_loader.hpp"
 namespace zkb {
 
+// bumped whenever any device buffer is (re)allocated or released: a captured CUDA graph holds raw device addresses and is only
+// replayed while the epoch it was captured in is still current
+static std::atomic<uint64_t> g_alloc_epoch{1};
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     void ensure(size_t bytes) {
         if (bytes <= cap) return;
+        g_alloc_epoch++;
         if (p) { cudaFree(p); p = nullptr; cap = 0; }
         cudaError_t e = cudaMalloc(&p, bytes);
         if (e != cudaSuccess) { p = nullptr; throw CudaError(std::string("cudaMalloc of ") + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e)); }
         cap = bytes;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) { cudaFree(p); g_alloc_epoch++; } p = nullptr; cap = 0; }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -128,6 +134,12 @@ struct zkb_ctx {
     struct FsTree { size_t o_rows, o_paths; uint32_t width, depth; };
     struct FsLayout { size_t o_ood = 0, o_rem = 0, host_bytes = 0, o_coef = 0, o_gamma = 0, o_scr = 0, total = 0; uint32_t rem_cap = 0; std::vector<FsTree> trees; } fs;
     DevBuf d_fs, d_in, d_rem_coef;      // d_in: per-proof inputs [assertion values na][AIR params]
+    DevBuf d_eval_pack;                 // shape-only evaluator inputs (periodic column, assertion columns / indices) and their host copy
+    std::vector<uint8_t> eval_pack;
+    // ---- CUDA graphs for small proofs: the whole enqueue sequence of a shape, replayed with one launch ---------------------
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t epoch = 0; uint32_t seen = 0; uint64_t launches = 0; };
+    std::map<std::string, GraphEntry> graphs;
+    bool capturing = false;
     DevBuf d_div;                       // divisor table of the current shape (k_build_divisors) and the shape it belongs to
     std::vector<uint64_t> div_key;
     uint8_t* h_out = nullptr;           // pinned landing area of the final download
@@ -199,12 +211,13 @@ struct zkb_ctx {
         cudaStreamSynchronize(stream);
         for (DevBuf* b : {&d_trace, &d_bufA, &d_bufB, &d_tmp1, &d_tmp2, &d_lde, &d_tree, &d_small, &d_comp_evals, &d_comp_lde, &d_comp_tree,
                           &d_ab, &d_ab_lde, &d_deep, &d_roots_lo, &d_roots_hi, &d_inv3_lo, &d_inv3_hi, &d_pow3, &d_aux, &d_gather, &d_user_trace, &d_flags,
-                          &d_lde_rows, &d_mg_a, &d_mg_b, &d_bnd_coef, &d_bnd_lde, &d_fs, &d_in, &d_rem_coef, &d_div})
+                          &d_lde_rows, &d_mg_a, &d_mg_b, &d_bnd_coef, &d_bnd_lde, &d_fs, &d_in, &d_rem_coef, &d_div, &d_eval_pack})
             b->release();
         if (comm) { g_nccl.CommDestroy(comm); comm = nullptr; }
         for (auto& b : d_fri_evals) b.release();
         for (auto& b : d_fri_tree) b.release();
         for (auto& kv : tw_cache) kv.second.release();
+        for (auto& kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         if (ev_ok) { for (auto& pr : tev) for (auto& x : pr) cudaEventDestroy(x); for (auto& x : ev_group) cudaEventDestroy(x); cudaStreamDestroy(copy_stream); cudaStreamDestroy(xchg_stream); }
         if (h_stage) cudaFreeHost(h_stage);
         if (h_out) cudaFreeHost(h_out);
@@ -227,8 +240,8 @@ struct zkb_ctx {
         CK(cudaMemcpyAsync(dst, h_stage + h_stage_used, bytes, cudaMemcpyHostToDevice, stream));
         h_stage_used += need;
     }
-    void t_begin(int st) { CK(cudaEventRecord(tev[st][0], stream)); }
-    void t_end(int st) { CK(cudaEventRecord(tev[st][1], stream)); trec[st] = true; times_valid = false; }
+    void t_begin(int st) { if (!capturing) CK(cudaEventRecord(tev[st][0], stream)); }
+    void t_end(int st) { if (!capturing) { CK(cudaEventRecord(tev[st][1], stream)); trec[st] = true; times_valid = false; } }
     void collect_times() {
         if (times_valid) return;
         CK(cudaSetDevice(device));
@@ -473,6 +486,7 @@ struct zkb_ctx {
             d_fs.ensure(fs.total);
             if (h_out_cap < fs.host_bytes) {
                 if (h_out) { cudaFreeHost(h_out); h_out = nullptr; h_out_cap = 0; }
+                g_alloc_epoch++;
                 CK(cudaHostAlloc((void**)&h_out, fs.host_bytes, cudaHostAllocDefault));
                 h_out_cap = fs.host_bytes;
             }
@@ -797,13 +811,18 @@ struct zkb_ctx {
         static const std::vector<HF> no_per;
         const std::vector<HF>& per = air.id == ZKB_AIR_ID_MIMC ? per_cache : no_per;
         // pack the shape-dependent small arrays into one device buffer
-        size_t off_z = 0, off_p = off_z + ce * 16, off_col = off_p + per.size() * 16, off_sel = off_col + (size_t)nl * 4, total = off_sel + (size_t)nl * 4 + 16;
+        size_t off_p = 0, off_col = off_p + per.size() * 16, off_sel = off_col + (size_t)nl * 4, total = off_sel + (size_t)nl * 4 + 16;
         std::vector<uint8_t> pack(total);
-        memcpy(&pack[off_z], zinv.data(), ce * 16); if (!per.empty()) memcpy(&pack[off_p], per.data(), per.size() * 16);
+        if (!per.empty()) memcpy(&pack[off_p], per.data(), per.size() * 16);
         if (nl) { memcpy(&pack[off_col], acol.data(), (size_t)nl * 4); memcpy(&pack[off_sel], asel.data(), (size_t)nl * 4); }
-        d_aux.ensure(total);
-        h2d_small(d_aux.p, pack.data(), total);
-        uint8_t* base = d_aux.as<uint8_t>();
+        // shape-only data: uploaded when it changes, not per proof (and never inside a graph capture)
+        if (pack != eval_pack || d_eval_pack.cap < total) {
+            if (capturing) throw StateError("evaluator tables changed during a graph capture");
+            d_eval_pack.ensure(total);
+            h2d_small(d_eval_pack.p, pack.data(), total);
+            eval_pack = pack;
+        }
+        uint8_t* base = d_eval_pack.as<uint8_t>();
         const fe* coef = fs_fe(fs.o_coef);
         p.tcoef = coef + (windowed ? col0 : 0); p.a_coef = coef + nt; p.a_val = d_aval(); p.params = d_params();
         p.periodic = (const fe*)(base + off_p);
@@ -812,12 +831,15 @@ struct zkb_ctx {
         p.out = out;
         {
             if (build_div) {
+                if (capturing) throw StateError("divisor table changed during a graph capture");
                 d_div.ensure((size_t)(ng + 1) * n * ce * 16);
+                d_aux.ensure(ce * 16);
+                h2d_small(d_aux.p, zinv.data(), ce * 16);
                 DivParams dp{};
                 dp.log_cen = log_n + log_ce; dp.log_ce = log_ce; dp.n_groups = ng;
                 for (uint32_t gi = 0; gi < ng; gi++) dp.g_point[gi] = to_fe(g.pow((u128)gsteps[gi]));
                 dp.g_last = to_fe(g.pow((u128)(n - 1)));
-                dp.zinv = (const fe*)(base + off_z);
+                dp.zinv = d_aux.as<fe>();
                 dp.roots = roots; dp.log_tab = log_tab;
                 dp.out = d_div.as<fe>();
                 const uint64_t threads = (n * ce) / ZKB_DIV_RPT;
@@ -1259,13 +1281,84 @@ struct zkb_ctx {
     std::vector<uint8_t> prove(const zkb_air_desc* desc, const uint8_t* const* cols, const fe* d_trace_in, uint64_t force_nonce,
                                bool sharded = false) {
         static const bool host_prof = getenv("ZKB_HOST_PROFILE") != nullptr;   // diagnostics: host phases of a proof on stderr
+        static const bool graphs_on = !(getenv("ZKB_GRAPH") && getenv("ZKB_GRAPH")[0] == '0');
         const auto hp0 = std::chrono::steady_clock::now();
         begin(desc);
         const auto hp1 = std::chrono::steady_clock::now();
         t_begin(TS_TOTAL);
         if (sharded) return prove_sharded(cols, d_trace_in, force_nonce);
+        if (!d_trace_in && !cols) throw InvalidArg("null trace columns");
+        // Small proofs are launch-bound (tens of 3-8 us kernels): from the second proof of a shape on, the whole enqueue sequence
+        // is captured into a CUDA graph and replayed with one launch.  What varies between proofs of a shape — coin seed,
+        // assertion values, AIR parameters (uploaded by begin()) and the trace — sits at fixed device addresses.
+        const bool small = graphs_on && !force_nonce && ((air.lde_size() * air.w) >> 22) == 0;
+        if (!small) enqueue_proof(cols, d_trace_in, force_nonce);
+        else {
+            const fe* src = d_trace_in ? d_trace_in : upload_cols(cols, air.w, air.n, d_trace);
+            std::string key((const char*)desc, offsetof(zkb_air_desc, pub_elems));
+            key.append((const char*)desc->assert_cols, desc->n_assertions * 4).append((const char*)desc->assert_steps, desc->n_assertions * 8);
+            key.append((const char*)&desc->n_params, 8).append((const char*)&src, sizeof(src));
+            GraphEntry& g = graphs[key];
+            if (g.exec && g.epoch != g_alloc_epoch.load()) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+            if (g.exec) {
+                CK(cudaGraphLaunch(g.exec, stream));
+                launches += g.launches;
+            } else if (g.seen == 0) {
+                g.seen = 1;                              // first proof of a shape: eager (buffers, tables and caches get built)
+                enqueue_proof(nullptr, src, 0);
+            } else {
+                const uint64_t e0 = g_alloc_epoch.load(), l0 = launches;
+                cudaGraph_t graph = nullptr;
+                bool ok = false;
+                // captured on the context's side stream (the caller's stream may be the legacy default stream, which cannot be
+                // captured); nothing executes during a capture, and the instantiated graph is launched into the caller's stream
+                cudaStream_t user_stream = stream;
+                stream = copy_stream;
+                cudaError_t ce = cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed);
+                if (ce == cudaSuccess) {
+                    capturing = true;
+                    try { enqueue_proof(nullptr, src, 0); ok = true; } catch (const std::exception&) {}
+                    capturing = false;
+                    ce = cudaStreamEndCapture(stream, &graph);
+                }
+                stream = user_stream;
+                if (ok && ce == cudaSuccess && graph && g_alloc_epoch.load() == e0) {
+                    cudaGraphExec_t ex = nullptr;
+                    if (cudaGraphInstantiate(&ex, graph, 0) == cudaSuccess) { g.exec = ex; g.epoch = e0; g.launches = launches - l0; }
+                }
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();                      // a failed capture leaves a sticky-looking (but cleared here) error
+                launches = l0;
+                begin_stage_reset();
+                if (g.exec) { CK(cudaGraphLaunch(g.exec, stream)); launches += g.launches; }
+                else { g.seen = 0; enqueue_proof(nullptr, src, 0); }   // could not capture (e.g. a buffer grew): run it eagerly
+            }
+        }
+        t_end(TS_TOTAL);
+        const auto hp2 = std::chrono::steady_clock::now();
+        // small proofs: spin on the stream (a blocking wait costs a wake-up, tens of microseconds, which is a large part of a
+        // sub-millisecond proof); large proofs: sleep on the event so that a lane does not burn a host core while the GPU works
+        if ((air.lde_size() * air.w) >> 22) { CK(cudaEventRecord(ev_done, stream)); CK(cudaEventSynchronize(ev_done)); }
+        else CK(cudaStreamSynchronize(stream));
+        const auto hp3 = std::chrono::steady_clock::now();
+        stage = ST_QUERY;
+        std::vector<uint8_t> out = assemble_proof();
+        if (host_prof) {
+            const auto hp4 = std::chrono::steady_clock::now();
+            auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+            fprintf(stderr, "[zkb host] begin %.1f us, enqueue %.1f us, wait %.1f us, assemble %.1f us, launches so far %llu\n", us(hp0, hp1), us(hp1, hp2),
+                    us(hp2, hp3), us(hp3, hp4), (unsigned long long)launches);
+        }
+        return out;
+    }
+    // host-side stage bookkeeping back to "begun" (after a capture walked it through all stages without executing anything)
+    void begin_stage_reset() { stage = ST_BEGUN; fri_layer = 0; fri_committed = false; }
+
+    // Everything between "the trace is available" and "the last byte of the proof is on its way to the host": no host
+    // synchronisation and no per-proof upload — the sequence depends on the shape only, which is what makes it capturable.
+    void enqueue_proof(const uint8_t* const* cols, const fe* d_trace_in, uint64_t force_nonce) {
         if (d_trace_in) trace_commit_dev(nullptr, d_trace_in);
-        else { if (!cols) throw InvalidArg("null trace columns"); trace_commit_dev(cols, nullptr); }
+        else trace_commit_dev(cols, nullptr);
         fs_after_trace_root(d_tree.as<uint32_t>() + 8, nullptr);       // channel.commit_trace; get_constraint_composition_coeffs
         constraints_eval_dev();
         constraints_commit_dev();
@@ -1318,23 +1411,7 @@ struct zkb_ctx {
             }
         }
         t_end(TS_QUERY);
-        t_end(TS_TOTAL);
         CK(cudaMemcpyAsync(h_out, d_fs.p, fs.host_bytes, cudaMemcpyDeviceToHost, stream));
-        const auto hp2 = std::chrono::steady_clock::now();
-        // small proofs: spin on the stream (a blocking wait costs a wake-up, tens of microseconds, which is a large part of a
-        // sub-millisecond proof); large proofs: sleep on the event so that a lane does not burn a host core while the GPU works
-        if ((air.lde_size() * air.w) >> 22) { CK(cudaEventRecord(ev_done, stream)); CK(cudaEventSynchronize(ev_done)); }
-        else CK(cudaStreamSynchronize(stream));
-        const auto hp3 = std::chrono::steady_clock::now();
-        stage = ST_QUERY;
-        std::vector<uint8_t> out = assemble_proof();
-        if (host_prof) {
-            const auto hp4 = std::chrono::steady_clock::now();
-            auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
-            fprintf(stderr, "[zkb host] begin %.1f us, enqueue %.1f us, wait %.1f us, assemble %.1f us, launches so far %llu\n", us(hp0, hp1), us(hp1, hp2),
-                    us(hp2, hp3), us(hp3, hp4), (unsigned long long)launches);
-        }
-        return out;
     }
 
     // Proof assembly from the single download: sort / dedup the positions (get_query_positions), fold them per FRI layer
