@@ -147,9 +147,11 @@ __device__ __forceinline__ fe fs_pow(fe b, uint32_t e) {
 // channel.commit_trace(root) + get_constraint_composition_coeffs() (one draw alpha; transition coefficients alpha^0.., boundary
 // coefficients continuing over the assertions sorted by (step, column)).  digest == nullptr: alpha was provided by the host
 // (staged API) and is already in ts->alpha.  coef[0 .. nt + na) = alpha^i.
-__global__ void __launch_bounds__(ZKB_FS_THREADS) k_fs_trace_root(DevTs* ts, const uint32_t* __restrict__ digest, uint32_t n_coef, fe* __restrict__ coef) {
+__global__ void __launch_bounds__(ZKB_FS_THREADS) k_fs_trace_root(DevTs* ts, const uint32_t* __restrict__ digest, uint32_t n_coef, fe* __restrict__ coef,
+                                                                 uint32_t* __restrict__ degree_flag) {
     __shared__ uint4 s_alpha;
     if (threadIdx.x == 0) {
+        *degree_flag = 0;   // raised by k_scale_pow if the composition polynomial does not fit (constraints_commit)
         if (digest) {
             uint32_t seed[8], d[8];
 #pragma unroll
@@ -261,11 +263,17 @@ __global__ void k_fs_fri_root(DevTs* ts, const uint32_t* __restrict__ digest, ui
     ts->fri_alpha[layer] = fs_draw(seed, &ts->coin_failed);
 }
 
-// FriProver::set_remainder: coef = the last layer interpolated over 3*<w_M> (already scaled); keep the first rs coefficients,
-// store them REVERSED, commit with hash_elements, reseed.  with_coin = 0: hash only (staged API).
-__global__ void __launch_bounds__(ZKB_FS_THREADS) k_fs_remainder(DevTs* ts, const fe* __restrict__ coef, uint32_t rs, fe* __restrict__ rem, uint32_t with_coin) {
+// FriProver::set_remainder: coef = the last layer after the inverse transform; the first rs coefficients are scaled here
+// (interpolation over the coset 3*<w_M>: coefficient m times scale * 3^-m, scale = 1/M), stored REVERSED,
+// committed with hash_elements, and the coin is reseeded.  with_coin = 0: hash only (staged API).
+__global__ void __launch_bounds__(ZKB_FS_THREADS) k_fs_remainder(DevTs* ts, const fe* __restrict__ coef, uint32_t rs, fe* __restrict__ rem, uint32_t with_coin,
+                                                                const fe* __restrict__ inv3_lo, const fe* __restrict__ inv3_hi, uint32_t inv3_l1, fe scale) {
     __shared__ uint32_t cvs[16][8];
-    for (uint32_t i = threadIdx.x; i < rs; i += blockDim.x) fe_store(rem + i, fe_load(coef + (rs - 1 - i)));
+    for (uint32_t i = threadIdx.x; i < rs; i += blockDim.x) {
+        const uint32_t m = rs - 1 - i;
+        const fe f = fe_mul(fe_mul(fe_ldg(inv3_lo + (m & ((1u << inv3_l1) - 1u))), fe_ldg(inv3_hi + (m >> inv3_l1))), scale);
+        fe_store(rem + i, fe_mul(fe_load(coef + m), f));
+    }
     __syncthreads();
     uint32_t h[8];
     fs_hash_elems_block(rem, rs, cvs, h);

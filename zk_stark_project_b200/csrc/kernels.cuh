@@ -850,6 +850,45 @@ __global__ void k_gather_fri_rows(const fe* __restrict__ e, uint64_t rows, const
     const uint32_t q = idx >> 4, j = idx & 15;
     fe_store(out + idx, fe_load(e + (__ldg(pos + q) & (uint32_t)(rows - 1)) + (uint64_t)j * rows));
 }
+// All openings of a one-shot proof in ONE launch (blockIdx.y = commitment): rows at the raw query positions plus the full
+// authentication path of each — k_gather_lde_rows / k_gather_fri_rows / k_gather_paths fused, because for small proofs every
+// launch is a measurable part of the latency.  Commitments 0, 1: LDE matrices (trace, constraint composition); 2 + l: FRI layer l.
+#define ZKB_MAX_OPEN 18
+struct OpenJobs {
+    uint32_t n_trees, q;
+    const uint32_t* pos;                 // raw positions (device transcript)
+    LdeMat mat[2];
+    const fe* fri_evals[ZKB_MAX_OPEN - 2];
+    uint64_t fri_rows[ZKB_MAX_OPEN - 2];
+    const uint32_t* heap[ZKB_MAX_OPEN];
+    uint32_t depth[ZKB_MAX_OPEN], width[ZKB_MAX_OPEN];
+    fe* rows_out[ZKB_MAX_OPEN];
+    uint32_t* paths_out[ZKB_MAX_OPEN];
+};
+__global__ void __launch_bounds__(128) k_open_all(const OpenJobs J) {
+    const uint32_t t = blockIdx.y;
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t w = J.width[t], depth = J.depth[t];
+    const uint32_t nrow = J.q * w, npath = J.q * depth * 2;
+    if (idx < nrow) {
+        const uint32_t q = idx / w, j = idx - q * w;
+        const uint32_t r = __ldg(J.pos + q);
+        if (t < 2) {
+            const LdeMat& m = J.mat[t];
+            const uint32_t k = r & ((1u << m.log_beta) - 1u), i = r >> m.log_beta;
+            fe_store(J.rows_out[t] + idx, fe_load(m.data + lde_addr(m, k, i, j)));
+        } else {
+            const uint64_t rows = J.fri_rows[t - 2];
+            fe_store(J.rows_out[t] + idx, fe_load(J.fri_evals[t - 2] + (r & (uint32_t)(rows - 1)) + (uint64_t)j * rows));
+        }
+    } else if (idx - nrow < npath) {
+        const uint32_t tt = idx - nrow;
+        const uint32_t half = tt & 1u, ql = tt >> 1, q = ql / depth, level = ql - q * depth;
+        const uint64_t node = ((((uint64_t)1 << depth) + (__ldg(J.pos + q) & ((1u << depth) - 1u))) >> level) ^ 1ull;
+        reinterpret_cast<uint4*>(J.paths_out[t])[tt] = reinterpret_cast<const uint4*>(J.heap[t])[node * 2 + half];
+    }
+}
+
 // Merkle authentication nodes: out[i] = digests[idx[i]]
 __global__ void k_gather_digests(const uint32_t* __restrict__ digests, const uint64_t* __restrict__ idx, uint32_t count, uint32_t* __restrict__ out) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -484,6 +484,7 @@ struct zkb_ctx {
             fs.o_scr = off; off += 2 * (size_t)w * 16;
             fs.total = off;
             d_fs.ensure(fs.total);
+            d_flags.ensure(256);
             if (h_out_cap < fs.host_bytes) {
                 if (h_out) { cudaFreeHost(h_out); h_out = nullptr; h_out_cap = 0; }
                 g_alloc_epoch++;
@@ -747,7 +748,7 @@ struct zkb_ctx {
     void fs_upload(fe* dst, const HF& v) { h2d_small(dst, &v, 16); }
     void fs_after_trace_root(const uint32_t* digest, const HF* alpha) {
         if (!digest) fs_upload(&dts()->alpha, *alpha);
-        k_fs_trace_root<<<1, ZKB_FS_THREADS, 0, stream>>>(dts(), digest, air.num_transition() + (uint32_t)air.assertions.size(), fs_fe(fs.o_coef));
+        k_fs_trace_root<<<1, ZKB_FS_THREADS, 0, stream>>>(dts(), digest, air.num_transition() + (uint32_t)air.assertions.size(), fs_fe(fs.o_coef), d_flags.as<uint32_t>());
         check_launch();
     }
     void fs_after_constraint_root(const uint32_t* digest, const HF* zz) {
@@ -934,8 +935,7 @@ struct zkb_ctx {
             run_xform(x, d_tmp1, d_tmp2);
             // inv3tab covers exponents < 2^log_N >= ce*n
             // the c*n kept coefficients are scaled; the dropped tail must be zero, else the trace violates the AIR (flag in d_flags)
-            d_flags.ensure(256);
-            CK(cudaMemsetAsync(d_flags.p, 0, 4, stream));
+            // (the flag was cleared by k_fs_trace_root)
             k_scale_pow<<<(unsigned)((cen + 255) / 256), 256, 0, stream>>>(coef, cen, inv3tab, to_fe(HF::from_u64(cen).inv()), (uint64_t)c * n,
                                                                             d_flags.as<uint32_t>());
             check_launch();
@@ -1017,16 +1017,17 @@ struct zkb_ctx {
             k_col_sum<<<(cols + 31) / 32, dim3(32, 32), 0, stream>>>(part, chunks, cols, out);
             check_launch();
         };
-        k_ood_partial<<<(nch + nsub - 1) / nsub, 256, 0, stream>>>(d_polys, (uint32_t)n, wl, R, log_wq, dts(), sm + o_pz, sm + o_pzg);
+        // (a single chunk — traces of <= 64 rows — needs no column sums: the partials are the frame)
+        k_ood_partial<<<(nch + nsub - 1) / nsub, 256, 0, stream>>>(d_polys, (uint32_t)n, wl, R, log_wq, dts(), nch == 1 ? cur_out : sm + o_pz,
+                                                                   nch == 1 ? nxt_out : sm + o_pzg);
         check_launch();
-        col_sum(sm + o_pz, nch, wl, cur_out);
-        col_sum(sm + o_pzg, nch, wl, nxt_out);
+        if (nch > 1) { col_sum(sm + o_pz, nch, wl, cur_out); col_sum(sm + o_pzg, nch, wl, nxt_out); }
         // H_i(z) from the composition column coefficients (still in d_bufA; replicated on every rank)
         {
             dim3 grid((nt + 255) / 256, c);
-            k_poly_eval_partial<<<grid, 256, 0, stream>>>(d_bufA.as<fe>(), (uint32_t)n, Q, dts(), sm + o_hp);
+            k_poly_eval_partial<<<grid, 256, 0, stream>>>(d_bufA.as<fe>(), (uint32_t)n, Q, dts(), nt == 1 ? frame + 2 * (size_t)w : sm + o_hp);
             check_launch();
-            col_sum(sm + o_hp, nt, c, frame + 2 * (size_t)w);
+            if (nt > 1) col_sum(sm + o_hp, nt, c, frame + 2 * (size_t)w);
         }
         if (mg_active) {
             // per-rank [cur wl][next wl] blocks -> the global frame, put back on the device for k_fs_ood
@@ -1172,10 +1173,8 @@ struct zkb_ctx {
         d_rem_coef.ensure(M * 16);
         Xform x{fri_cur_evals(), 1, 0, d_rem_coef.as<fe>(), 1, 0, 1, log2u(M), true, false, 0, false, HF()};
         run_xform(x, d_tmp1, d_tmp2);
-        d_flags.ensure(256);
-        k_scale_pow<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(d_rem_coef.as<fe>(), M, inv3tab, to_fe(HF::from_u64(M).inv()), M, d_flags.as<uint32_t>() + 8);
-        check_launch();
-        k_fs_remainder<<<1, ZKB_FS_THREADS, 0, stream>>>(dts(), d_rem_coef.as<fe>(), rs, fs_fe(fs.o_rem), with_coin ? 1u : 0u);
+        k_fs_remainder<<<1, ZKB_FS_THREADS, 0, stream>>>(dts(), d_rem_coef.as<fe>(), rs, fs_fe(fs.o_rem), with_coin ? 1u : 0u, inv3tab.lo, inv3tab.hi, inv3tab.l1,
+                                                         to_fe(HF::from_u64(M).inv()));
         check_launch();
         stage = ST_FRI_DONE;
     }
@@ -1386,29 +1385,28 @@ struct zkb_ctx {
         const uint32_t q = air.num_queries;
         k_fs_positions<<<1, ZKB_FS_THREADS, 0, stream>>>(dts(), q, (uint32_t)(air.lde_size() - 1));   // get_query_positions
         check_launch();
-        {   // TraceLde::query, ConstraintCommitment::query, FriProver::build_proof at the raw positions
-            const uint32_t* dpos = dts()->positions;
+        {   // TraceLde::query, ConstraintCommitment::query, FriProver::build_proof at the raw positions: one launch
+            OpenJobs J{};
             uint8_t* base = d_fs.as<uint8_t>();
+            J.n_trees = (uint32_t)fs.trees.size(); J.q = q; J.pos = dts()->positions;
+            J.mat[0] = lde_mat(); J.mat[1] = comp_mat();
+            uint32_t items = 0;
             for (size_t t = 0; t < fs.trees.size(); t++) {
                 const FsTree& tr = fs.trees[t];
-                const uint32_t th = q * tr.width;
-                fe* drows = (fe*)(base + tr.o_rows);
-                const uint32_t* heap;
-                if (t == 0) { k_gather_lde_rows<<<(th + 127) / 128, 128, 0, stream>>>(lde_mat(), dpos, q, drows); heap = d_tree.as<uint32_t>(); }
-                else if (t == 1) { k_gather_lde_rows<<<(th + 127) / 128, 128, 0, stream>>>(comp_mat(), dpos, q, drows); heap = d_comp_tree.as<uint32_t>(); }
+                J.depth[t] = tr.depth; J.width[t] = tr.width;
+                J.rows_out[t] = (fe*)(base + tr.o_rows); J.paths_out[t] = (uint32_t*)(base + tr.o_paths);
+                if (t == 0) J.heap[t] = d_tree.as<uint32_t>();
+                else if (t == 1) J.heap[t] = d_comp_tree.as<uint32_t>();
                 else {
                     const uint32_t l = (uint32_t)t - 2;
-                    const fe* e = l == 0 ? d_deep.as<fe>() : d_fri_evals[l].as<fe>();
-                    k_gather_fri_rows<<<(th + 127) / 128, 128, 0, stream>>>(e, fri_domain(l) / 16, dpos, q, drows);
-                    heap = d_fri_tree[l].as<uint32_t>();
+                    J.fri_evals[l] = l == 0 ? d_deep.as<fe>() : d_fri_evals[l].as<fe>();
+                    J.fri_rows[l] = fri_domain(l) / 16;
+                    J.heap[t] = d_fri_tree[l].as<uint32_t>();
                 }
-                check_launch();
-                const uint32_t pt = q * tr.depth * 2;
-                if (pt) {   // (a one-leaf tree has no authentication nodes)
-                    k_gather_paths<<<(pt + 127) / 128, 128, 0, stream>>>(heap, tr.depth, dpos, q, (1u << tr.depth) - 1u, (uint32_t*)(base + tr.o_paths));
-                    check_launch();
-                }
+                items = std::max(items, q * tr.width + q * tr.depth * 2);
             }
+            k_open_all<<<dim3((items + 127) / 128, J.n_trees), 128, 0, stream>>>(J);
+            check_launch();
         }
         t_end(TS_QUERY);
         CK(cudaMemcpyAsync(h_out, d_fs.p, fs.host_bytes, cudaMemcpyDeviceToHost, stream));
