@@ -1296,7 +1296,9 @@ struct zkb_ctx {
             const fe* src = d_trace_in ? d_trace_in : upload_cols(cols, air.w, air.n, d_trace);
             std::string key((const char*)desc, offsetof(zkb_air_desc, pub_elems));
             key.append((const char*)desc->assert_cols, desc->n_assertions * 4).append((const char*)desc->assert_steps, desc->n_assertions * 8);
-            key.append((const char*)&desc->n_params, 8).append((const char*)&src, sizeof(src));
+            // AIR parameters are part of the key: the MiMC round constants are baked into the evaluator's periodic-column table,
+            // which a replay does not rebuild (the aggregation factor k is read from the per-proof inputs either way)
+            key.append((const char*)&desc->n_params, 8).append((const char*)desc->params, desc->n_params * 16).append((const char*)&src, sizeof(src));
             GraphEntry& g = graphs[key];
             if (g.exec && g.epoch != g_alloc_epoch.load()) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
             if (g.exec) {
