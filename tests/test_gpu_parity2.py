@@ -210,6 +210,15 @@ def test_graph_replay_small_proofs(oracle):
         mair = m.describe(mt)
         got, _ = ctx.prove_host(mair, np.ascontiguousarray(mt.data).ctypes.data)
         assert got == oracle.prove(mair, mt.to_bytes())[0], f"mimc proof {rnd} differs"
+    # same shape, different round constants: the periodic column is baked into the evaluator tables, so this must not replay
+    # the graph captured for the default constants
+    for rnd in range(3):
+        rc = [(7 * rnd + 3) * (i + 1) * 10**6 for i in range(64)]
+        m = Z.MimcProver(T.options(blowup=8, grinding=5), [j + 1 for j in range(4)], 256, round_constants=rc)
+        mt = m.build_trace()
+        mair = m.describe(mt)
+        got, _ = ctx.prove_host(mair, np.ascontiguousarray(mt.data).ctypes.data)
+        assert got == oracle.prove(mair, mt.to_bytes())[0], f"mimc proof with custom round constants {rnd} differs"
     # a forced nonce takes the eager path and must still work on the same context
     p = T.aggregation_prover(16, T.options(grinding=0))
     tr = p.build_trace()

@@ -134,14 +134,15 @@ struct zkb_ctx {
     struct FsTree { size_t o_rows, o_paths; uint32_t width, depth; };
     struct FsLayout { size_t o_ood = 0, o_rem = 0, host_bytes = 0, o_coef = 0, o_gamma = 0, o_scr = 0, total = 0; uint32_t rem_cap = 0; std::vector<FsTree> trees; } fs;
     DevBuf d_fs, d_in, d_rem_coef;      // d_in: per-proof inputs [assertion values na][AIR params]
-    DevBuf d_eval_pack;                 // shape-only evaluator inputs (periodic column, assertion columns / indices) and their host copy
-    std::vector<uint8_t> eval_pack;
+    // shape-only evaluator inputs (periodic column, assertion columns / indices) and divisor tables (k_build_divisors), kept per
+    // distinct shape so that captured graphs of several shapes stay valid side by side
+    std::map<std::string, DevBuf> pack_cache;
+    std::map<std::vector<uint64_t>, DevBuf> div_cache;
+    size_t pack_cache_bytes = 0, div_cache_bytes = 0;
     // ---- CUDA graphs for small proofs: the whole enqueue sequence of a shape, replayed with one launch ---------------------
     struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t epoch = 0; uint32_t seen = 0; uint64_t launches = 0; };
     std::map<std::string, GraphEntry> graphs;
     bool capturing = false;
-    DevBuf d_div;                       // divisor table of the current shape (k_build_divisors) and the shape it belongs to
-    std::vector<uint64_t> div_key;
     uint8_t* h_out = nullptr;           // pinned landing area of the final download
     size_t h_out_cap = 0;
     cudaEvent_t ev_done = nullptr;      // blocking-sync event: the host thread sleeps instead of spinning while the device works
@@ -211,12 +212,14 @@ struct zkb_ctx {
         cudaStreamSynchronize(stream);
         for (DevBuf* b : {&d_trace, &d_bufA, &d_bufB, &d_tmp1, &d_tmp2, &d_lde, &d_tree, &d_small, &d_comp_evals, &d_comp_lde, &d_comp_tree,
                           &d_ab, &d_ab_lde, &d_deep, &d_roots_lo, &d_roots_hi, &d_inv3_lo, &d_inv3_hi, &d_pow3, &d_aux, &d_gather, &d_user_trace, &d_flags,
-                          &d_lde_rows, &d_mg_a, &d_mg_b, &d_bnd_coef, &d_bnd_lde, &d_fs, &d_in, &d_rem_coef, &d_div, &d_eval_pack})
+                          &d_lde_rows, &d_mg_a, &d_mg_b, &d_bnd_coef, &d_bnd_lde, &d_fs, &d_in, &d_rem_coef})
             b->release();
         if (comm) { g_nccl.CommDestroy(comm); comm = nullptr; }
         for (auto& b : d_fri_evals) b.release();
         for (auto& b : d_fri_tree) b.release();
         for (auto& kv : tw_cache) kv.second.release();
+        for (auto& kv : pack_cache) kv.second.release();
+        for (auto& kv : div_cache) kv.second.release();
         for (auto& kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         if (ev_ok) { for (auto& pr : tev) for (auto& x : pr) cudaEventDestroy(x); for (auto& x : ev_group) cudaEventDestroy(x); cudaStreamDestroy(copy_stream); cudaStreamDestroy(xchg_stream); }
         if (h_stage) cudaFreeHost(h_stage);
@@ -791,7 +794,7 @@ struct zkb_ctx {
         // divisor table of the shape (k_build_divisors): cached until the trace length, the ce blowup or the assertion steps change
         std::vector<uint64_t> dkey{n, ce};
         dkey.insert(dkey.end(), gsteps.begin(), gsteps.end());
-        const bool build_div = dkey != div_key;
+        const bool build_div = div_cache.find(dkey) == div_cache.end();
         // 1/(x^n - 1) on the cosets used by the ce domain: x^n = 3^n * w_beta^k, k = kc * beta/ce   (input of the table build only)
         std::vector<HF> zinv(ce);
         if (build_div) {
@@ -816,14 +819,27 @@ struct zkb_ctx {
         std::vector<uint8_t> pack(total);
         if (!per.empty()) memcpy(&pack[off_p], per.data(), per.size() * 16);
         if (nl) { memcpy(&pack[off_col], acol.data(), (size_t)nl * 4); memcpy(&pack[off_sel], asel.data(), (size_t)nl * 4); }
-        // shape-only data: uploaded when it changes, not per proof (and never inside a graph capture)
-        if (pack != eval_pack || d_eval_pack.cap < total) {
-            if (capturing) throw StateError("evaluator tables changed during a graph capture");
-            d_eval_pack.ensure(total);
-            h2d_small(d_eval_pack.p, pack.data(), total);
-            eval_pack = pack;
+        // shape-only data: uploaded once per distinct content and kept (a captured graph of that shape keeps reading it), never
+        // per proof and never inside a graph capture
+        DevBuf* packbuf;
+        {
+            const std::string pk((const char*)pack.data(), pack.size());
+            auto it = pack_cache.find(pk);
+            if (it == pack_cache.end()) {
+                if (capturing) throw StateError("evaluator tables changed during a graph capture");
+                if (pack_cache_bytes + total > ((size_t)64 << 20)) {
+                    CK(cudaStreamSynchronize(stream));
+                    for (auto& kv : pack_cache) kv.second.release();
+                    pack_cache.clear(); pack_cache_bytes = 0;
+                }
+                DevBuf& b = pack_cache[pk];
+                b.ensure(total);
+                pack_cache_bytes += total;
+                h2d_small(b.p, pack.data(), total);
+                packbuf = &b;
+            } else packbuf = &it->second;
         }
-        uint8_t* base = d_eval_pack.as<uint8_t>();
+        uint8_t* base = packbuf->as<uint8_t>();
         const fe* coef = fs_fe(fs.o_coef);
         p.tcoef = coef + (windowed ? col0 : 0); p.a_coef = coef + nt; p.a_val = d_aval(); p.params = d_params();
         p.periodic = (const fe*)(base + off_p);
@@ -831,9 +847,18 @@ struct zkb_ctx {
         p.per_mask = per.empty() ? 0 : (uint32_t)per.size() - 1;
         p.out = out;
         {
-            if (build_div) {
+            auto it = div_cache.find(dkey);
+            if (it == div_cache.end()) {
                 if (capturing) throw StateError("divisor table changed during a graph capture");
-                d_div.ensure((size_t)(ng + 1) * n * ce * 16);
+                const size_t bytes = (size_t)(ng + 1) * n * ce * 16;
+                if (div_cache_bytes + bytes > ((size_t)2 << 30) && !div_cache.empty()) {   // long-lived context, many shapes: start over
+                    CK(cudaStreamSynchronize(stream));
+                    for (auto& kv : div_cache) kv.second.release();
+                    div_cache.clear(); div_cache_bytes = 0;
+                }
+                DevBuf& tab = div_cache[dkey];
+                tab.ensure(bytes);
+                div_cache_bytes += bytes;
                 d_aux.ensure(ce * 16);
                 h2d_small(d_aux.p, zinv.data(), ce * 16);
                 DivParams dp{};
@@ -842,13 +867,12 @@ struct zkb_ctx {
                 dp.g_last = to_fe(g.pow((u128)(n - 1)));
                 dp.zinv = d_aux.as<fe>();
                 dp.roots = roots; dp.log_tab = log_tab;
-                dp.out = d_div.as<fe>();
+                dp.out = tab.as<fe>();
                 const uint64_t threads = (n * ce) / ZKB_DIV_RPT;
                 k_build_divisors<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(dp);
                 check_launch();
-                div_key = dkey;
-            }
-            p.div = d_div.as<fe>();
+                p.div = tab.as<fe>();
+            } else p.div = it->second.as<fe>();
         }
         // Boundary numerators.  Per-point sums cost nl multiplications at each of the ce*n points; combining the asserted
         // columns in coefficient space (nl per coefficient row) and extending the ng combined polynomials once costs
