@@ -343,15 +343,4 @@ __global__ void __launch_bounds__(ZKB_FS_THREADS) k_fs_positions(DevTs* ts, uint
     }
 }
 
-// Merkle authentication paths of `npos` leaves (positions masked into the tree's leaf range): out[(q * depth + level)] = the
-// sibling of leaf q's ancestor at `level` (level 0 = the sibling leaf).  heap[1] = root, heap[2^depth + l] = leaf l.
-__global__ void k_gather_paths(const uint32_t* __restrict__ heap, uint32_t depth, const uint32_t* __restrict__ pos, uint32_t npos, uint32_t mask,
-                               uint32_t* __restrict__ out) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;   // (q, level, half)
-    if (t >= npos * depth * 2) return;
-    const uint32_t half = t & 1u, ql = t >> 1, q = ql / depth, level = ql - q * depth;
-    const uint64_t node = ((((uint64_t)1 << depth) + (__ldg(pos + q) & mask)) >> level) ^ 1ull;
-    reinterpret_cast<uint4*>(out)[t] = reinterpret_cast<const uint4*>(heap)[node * 2 + half];
-}
-
 }  // namespace zkb
