@@ -339,7 +339,13 @@ def roofline_of(workload, n, w_local, beta, lde_ms, alg_lde, peak, peak_src, sha
         # what actually bounds K1/K2: integer issue.  Peak = register-resident radix-2 f128 butterflies/s of the shipped twiddle multiplier
         # (four pre-shifted copies) on this pool's B200, best occupancy / ILP setting (tools/mul_variants.cu variant F; no memory traffic at all)
         "compute_roofline": {"unit": "G butterflies/s", "peak": 270.5, "achieved": bf / (lde_ms * 1e-3) / 1e9,
-                             "frac": bf / (lde_ms * 1e-3) / 1e9 / 270.5, "source": "tools/mul_variants.cu variant F (251-270 G/s depending on ILP), profiles/r2_mul_variants.txt"},
+                             "frac": bf / (lde_ms * 1e-3) / 1e9 / 270.5, "source": "tools/mul_variants.cu variant F (251-270 G/s depending on ILP), profiles/r2_mul_variants.txt",
+                             # against the MACHINE rather than against the multiplier's own ceiling: instruction issue.  Both integer pipes take one
+                             # warp-instruction every two cycles per sub-partition, a balanced two-source mix issues 0.95/clk (profiles/r1_int_pipe_peaks.txt);
+                             # ncu on the shipped LDE passes: 0.53-0.54 (profiles/r2_ncu_ntt_hash_training_2p16.txt) - carry-chained multi-limb code
+                             # sits at 62-67 % of its binding pipe whatever the mix, so the lever left is the instruction count (69.4 per butterfly)
+                             "issue_slots": {"unit": "warp-instr/clk/SMSP", "achieved_ncu": 0.535, "peak_measured_balanced_mix": 0.95, "frac": 0.56,
+                                             "instr_per_butterfly": 69.4}},
     }
 
 
