@@ -151,6 +151,31 @@ __device__ __forceinline__ void b3_hash_elems(const fe* __restrict__ base, size_
 #pragma unroll
     for (int i = 0; i < 8; i++) out[i] = st0[i];
 }
+// Chaining value of chunk c (64 elements, the last one shorter) of the same strided element sequence; count > 64, so no chunk
+// is the root.  Used where a row's chunks are hashed by different threads (k_hash_lde_rows_split).
+__device__ __forceinline__ void b3_chunk_cv_elems(const fe* __restrict__ base, size_t stride, uint32_t count, uint32_t c, uint32_t cv[8],
+                                                  uint32_t bw, uint32_t bw_magic, size_t blk_stride) {
+    b3_iv(cv);
+    const uint32_t e0 = c * 64u;
+    const uint32_t ne = (count - e0) < 64u ? (count - e0) : 64u;
+    const uint32_t nblk = (ne + 3u) / 4u;
+    for (uint32_t b = 0; b < nblk; b++) {
+        uint32_t m[16];
+        const uint32_t eb = e0 + 4u * b;
+        const uint32_t nb = (e0 + ne - eb) < 4u ? (e0 + ne - eb) : 4u;
+#pragma unroll
+        for (uint32_t q = 0; q < 4; q++) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (q < nb) {
+                const uint32_t e = eb + q, blk = (e * bw_magic) >> 16;
+                v = *reinterpret_cast<const uint4*>(base + (size_t)blk * blk_stride + (size_t)(e - blk * bw) * stride);
+            }
+            m[4 * q] = v.x; m[4 * q + 1] = v.y; m[4 * q + 2] = v.z; m[4 * q + 3] = v.w;
+        }
+        const uint32_t flags = (b == 0 ? B3_CHUNK_START : 0u) | (b + 1 == nblk ? B3_CHUNK_END : 0u);
+        b3_compress(cv, m, c, nb * 16u, flags);
+    }
+}
 #endif
 
 // ---- host-side BLAKE3 for the channel (inputs are tiny: seeds, digests, OOD frames) ----------------

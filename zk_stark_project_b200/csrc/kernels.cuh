@@ -380,6 +380,55 @@ __global__ void __launch_bounds__(128) k_hash_lde_rows(const LdeMat m, uint32_t*
     o[0] = make_uint4(d[0], d[1], d[2], d[3]);
     o[1] = make_uint4(d[4], d[5], d[6], d[7]);
 }
+// The same leaves for a matrix of a few thousand rows (the aggregation proof: 512 rows x 120 columns): one thread per
+// (row, 1 KiB chunk) — a row's chunks are independent until their chaining values meet in the BLAKE3 tree, so a 1920-byte
+// row costs 16 + 1 dependent compressions instead of 31.  Four lanes per row; lanes past the row's chunk count idle.
+__global__ void __launch_bounds__(128) k_hash_lde_rows_split(const LdeMat m, uint32_t* __restrict__ leaves, uint64_t leaf0, uint32_t compact) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t c = (uint32_t)t & 3u;
+    const uint32_t lpf = lde_full_log_p(m), lt = m.log_n - lpf;
+    const uint32_t log_rows = m.log_kc + lt + (m.view == 0 ? lpf : m.log_p);
+    const bool live = ((t >> 2) >> log_rows) == 0;      // whole warps take part in the shuffles; dead rows hash row 0 and drop it
+    const uint64_t gid = live ? (t >> 2) : 0;
+    const uint32_t lslots = m.view == 0 ? lpf : m.log_p;
+    const uint32_t s = (uint32_t)gid & ((1u << lslots) - 1u);
+    const uint32_t panel = (uint32_t)(gid >> lslots);
+    const uint32_t slot = m.view == 0 ? s : ((m.q_self << m.log_p) + s);
+    const uint32_t k = m.k0 + (panel >> lt), t_low = panel & ((1u << lt) - 1u);
+    const uint32_t i = t_low + (slot << lt);
+    const uint64_t r = compact ? (((uint64_t)i << m.log_kc) + (k - m.k0)) : (((uint64_t)i << m.log_beta) + k - leaf0);
+    const uint32_t nchunks = (m.w + 63u) / 64u;         // 2..4 (the caller sends single-chunk rows to k_hash_lde_rows)
+    uint32_t cv[8], nb[8];
+    if (c < nchunks) b3_chunk_cv_elems(m.data + lde_row_base(m, k, i), (size_t)1 << m.log_p, m.w, c, cv, m.bw, m.bw_magic, m.blk_stride);
+    else {
+#pragma unroll
+        for (int q = 0; q < 8; q++) cv[q] = 0;
+    }
+    // tree: 2 chunks parent(0,1); 3 chunks parent(parent(0,1), 2); 4 chunks parent(parent(0,1), parent(2,3))
+#pragma unroll
+    for (int q = 0; q < 8; q++) nb[q] = __shfl_down_sync(0xffffffffu, cv[q], 1);
+    if (c == 0 || (c == 2 && nchunks == 4)) {
+        uint32_t o[8];
+        b3_parent(cv, nb, nchunks == 2, o);
+#pragma unroll
+        for (int q = 0; q < 8; q++) cv[q] = o[q];
+    }
+    if (nchunks > 2) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) nb[q] = __shfl_down_sync(0xffffffffu, cv[q], 2);
+        if (c == 0) {
+            uint32_t o[8];
+            b3_parent(cv, nb, true, o);
+#pragma unroll
+            for (int q = 0; q < 8; q++) cv[q] = o[q];
+        }
+    }
+    if (live && c == 0) {
+        uint4* o = reinterpret_cast<uint4*>(leaves + r * 8);
+        o[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+        o[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+    }
+}
 // multi-GPU: after an all-gather of per-rank compact arrays [src][i * kc + kl] (kc = stored cosets per rank), put item
 // (i, k = src*kc + kl) at natural LDE position i*beta + k.  `words` 32-bit words per item (8: digests, 4: field elements).
 __global__ void k_permute_coset_items(const uint32_t* __restrict__ gathered, uint32_t* __restrict__ out, uint32_t log_n, uint32_t log_beta,
@@ -549,12 +598,19 @@ __global__ void __launch_bounds__(128) k_build_divisors(const DivParams p) {
     }
 }
 
-// One thread per constraint-evaluation-domain point:  sum_c coef_c * transition_c(frame) * div[ng]  +  sum_g numerator_g * div[g]
+// One point of the constraint evaluation domain:  sum_c coef_c * transition_c(frame) * div[ng]  +  sum_g numerator_g * div[g].
+// LANES = 1: one thread per point (large domains: every SM is full of points).  LANES = 32: one warp per point, lanes stride
+// over the constraints and assertions and their partial results are added by shuffles — for domains of a few hundred points
+// (the aggregation proof: 64 points x 60 constraints + 120 assertions) the per-point chain of dependent loads is what the
+// proof waits for, not throughput.  Field addition is exact, so both variants store the same canonical element.
+template <int LANES>
 __global__ void __launch_bounds__(128) k_eval_constraints(const EvalParams p) {
     const LdeMat& m = p.lde;
     const uint64_t total = (uint64_t)1 << (m.log_n + p.log_ce);
-    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= total) return;
+    const uint64_t gthread = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t gid = LANES == 1 ? gthread : gthread / LANES;
+    const uint32_t lane = LANES == 1 ? 0u : (uint32_t)(threadIdx.x & (LANES - 1));
+    if (gid >= total) return;   // LANES = 32: warp-uniform
     const uint32_t lpf = lde_full_log_p(m), lt = m.log_n - lpf;
     const size_t cs = (size_t)1 << m.log_p;  // column stride
     const uint32_t ng = p.n_groups;
@@ -576,14 +632,14 @@ __global__ void __launch_bounds__(128) k_eval_constraints(const EvalParams p) {
     if (p.air_id == ZKB_AIR_AGGREGATION) {
         const uint32_t d = p.n_trans;
         const fe kf = fe_ldg(p.params);
-        for (uint32_t c = 0; c < d; c++) {
+        for (uint32_t c = lane; c < d; c += LANES) {
             fe dn = fe_sub(fe_load(nxt + c * cs), fe_load(cur + c * cs));
             fe ev = fe_sub(fe_mul(kf, dn), fe_load(nxt + (size_t)(c + d) * cs));
             acc288_mad(tacc, fe_ldg(p.tcoef + c), ev);
         }
     } else if (p.air_id == ZKB_AIR_MIMC) {
         const fe rc = fe_ldg(p.periodic + (ci & p.per_mask));
-        for (uint32_t c = 0; c < p.n_trans; c++) {
+        for (uint32_t c = lane; c < p.n_trans; c += LANES) {
             fe a1 = fe_add(fe_load(cur + c * cs), rc);
             fe a2 = fe_sqr(a1), a4 = fe_sqr(a2), a6 = fe_mul(a4, a2), a7 = fe_mul(a6, a1);
             fe ev = fe_sub(fe_load(nxt + c * cs), a7);
@@ -598,10 +654,10 @@ __global__ void __launch_bounds__(128) k_eval_constraints(const EvalParams p) {
     for (uint32_t g = 0; g < ng; g++) {
         fe sum;
         if (p.bnd_poly) {
-            sum = fe_load(bp + ((size_t)g << p.bnd.log_p));
+            sum = lane == 0 ? fe_load(bp + ((size_t)g << p.bnd.log_p)) : fe_zero();
         } else {
             acc288 bacc; acc288_zero(bacc);
-            for (uint32_t a = p.g_off[g]; a < p.g_off[g + 1]; a++) {
+            for (uint32_t a = p.g_off[g] + lane; a < p.g_off[g + 1]; a += LANES) {
                 const uint32_t ai = __ldg(p.a_sel + a);
                 fe v = fe_sub(fe_load(cur + (size_t)__ldg(p.a_col + a) * cs), fe_ldg(p.a_val + ai));
                 acc288_mad(bacc, fe_ldg(p.a_coef + ai), v);
@@ -609,6 +665,16 @@ __global__ void __launch_bounds__(128) k_eval_constraints(const EvalParams p) {
             sum = acc288_reduce(bacc);
         }
         res = fe_add(res, fe_mul(sum, fe_ldg(p.div + ((size_t)g << log_cen) + ci)));
+    }
+    if (LANES > 1) {   // every lane holds the terms of its constraints and assertions, each already times its divisor
+#pragma unroll
+        for (int off = LANES / 2; off > 0; off >>= 1) {
+            fe o;
+            o.x[0] = __shfl_down_sync(0xffffffffu, res.x[0], off); o.x[1] = __shfl_down_sync(0xffffffffu, res.x[1], off);
+            o.x[2] = __shfl_down_sync(0xffffffffu, res.x[2], off); o.x[3] = __shfl_down_sync(0xffffffffu, res.x[3], off);
+            res = fe_add(res, o);
+        }
+        if (lane != 0) return;
     }
     fe_store(p.out + ci, res);
 }
@@ -720,23 +786,25 @@ __global__ void __launch_bounds__(256) k_deep_combine(const fe* __restrict__ pol
         fe_store(ab + (size_t)warp * 2 + 1, fe_add(s, b));
     }
 }
-// k_deep_eval: each thread handles RPT rows (one Montgomery batch inversion per thread)
+// k_deep_eval: each thread handles ZKB_DEEP_RPT rows (one Montgomery batch inversion per thread); RPT = 1 for domains of a
+// few thousand rows, where the proof waits for one thread's chain (inversion + 6 multiplications per extra row), not for throughput
 #define ZKB_DEEP_RPT 8
 // compact = 1 (coset-sharded AB matrix): out index = i * (stored cosets) + local coset, else the natural position i*beta + k
+template <int RPT>
 __global__ void __launch_bounds__(128) k_deep_eval(const LdeMat m, const DevTs* __restrict__ ts, PowTab roots, uint32_t log_tab,
                                                    fe* __restrict__ out, uint32_t compact) {
-    const fe z = ts->z, zg = ts->zg, az = ts->az, abz = ts->abz, azg = ts->azg;
+    const fe z = ts->z, zg = ts->zg, abz = ts->abz, azg = ts->azg;
     const uint32_t log_N = m.log_n + m.log_beta;
     const uint64_t N = (uint64_t)1 << (m.log_n + m.log_kc);   // rows stored
-    const uint64_t nthreads = N / ZKB_DEEP_RPT;
+    const uint64_t nthreads = N / RPT;
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= nthreads) return;
     const uint32_t lt = m.log_n - m.log_p;
-    fe d[2 * ZKB_DEEP_RPT], pre[2 * ZKB_DEEP_RPT], n1[ZKB_DEEP_RPT], n2[ZKB_DEEP_RPT];
-    uint32_t rr[ZKB_DEEP_RPT];
+    fe d[2 * RPT], pre[2 * RPT], n1[RPT], n2[RPT];
+    uint32_t rr[RPT];
     fe acc = fe_one();
 #pragma unroll
-    for (int s = 0; s < ZKB_DEEP_RPT; s++) {
+    for (int s = 0; s < RPT; s++) {
         const uint64_t gid = tid + (uint64_t)s * nthreads;
         const uint32_t slot = (uint32_t)gid & ((1u << m.log_p) - 1u);
         const uint32_t panel = (uint32_t)(gid >> m.log_p);
@@ -757,7 +825,7 @@ __global__ void __launch_bounds__(128) k_deep_eval(const LdeMat m, const DevTs* 
     }
     fe ia = fe_inv(acc);
 #pragma unroll
-    for (int s = ZKB_DEEP_RPT - 1; s >= 0; s--) {
+    for (int s = RPT - 1; s >= 0; s--) {
         fe i2 = fe_mul(ia, pre[2 * s + 1]); ia = fe_mul(ia, d[2 * s + 1]);
         fe i1 = fe_mul(ia, pre[2 * s]); ia = fe_mul(ia, d[2 * s]);
         fe_store(out + rr[s], fe_add(fe_mul(n1[s], i1), fe_mul(n2[s], i2)));

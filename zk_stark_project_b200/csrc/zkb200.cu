@@ -579,7 +579,9 @@ struct zkb_ctx {
         t_end(TS_LDE);
         // K3: leaves
         t_begin(TS_LEAF);
-        k_hash_lde_rows<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(lde_mat(), d_tree.as<uint32_t>() + N * 8, 0, 0);
+        // few, wide rows: hash a row's 1 KiB chunks on separate lanes (a shorter chain of compressions, same digests)
+        if (N <= 8192 && w > 64) k_hash_lde_rows_split<<<(unsigned)((N * 4 + 127) / 128), 128, 0, stream>>>(lde_mat(), d_tree.as<uint32_t>() + N * 8, 0, 0);
+        else k_hash_lde_rows<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(lde_mat(), d_tree.as<uint32_t>() + N * 8, 0, 0);
         check_launch();
         t_end(TS_LEAF);
         // K4: tree
@@ -899,7 +901,9 @@ struct zkb_ctx {
             }
         }
         const uint64_t points = n * ce;
-        k_eval_constraints<<<(unsigned)((points + 127) / 128), 128, 0, stream>>>(p);
+        // a few hundred points cannot fill the GPU with one thread each: give every point a warp (same values, shorter chain)
+        if (points <= 4096 && !p.bnd_poly) k_eval_constraints<32><<<(unsigned)((points * 32 + 127) / 128), 128, 0, stream>>>(p);
+        else k_eval_constraints<1><<<(unsigned)((points + 127) / 128), 128, 0, stream>>>(p);
         check_launch();
     }
     // out[i] = sum over ranks of partial[i] (mod p), on every rank.  NCCL cannot add 128-bit field elements, so the reduction is
@@ -1108,8 +1112,8 @@ struct zkb_ctx {
         if (!mg_coset()) {
             Xform x{d_ab.as<fe>(), 2, 0, d_ab_lde.as<fe>(), 2, 0, 2, log_n, false, true, log_N, false, HF()};
             ab_log_p = run_xform(x, d_tmp1, d_tmp2);
-            const uint64_t threads = N / ZKB_DEEP_RPT;
-            k_deep_eval<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(ab_mat(), dts(), roots, log_tab, d_deep.as<fe>(), 0);
+            if (N <= 8192) k_deep_eval<1><<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(ab_mat(), dts(), roots, log_tab, d_deep.as<fe>(), 0);
+            else k_deep_eval<ZKB_DEEP_RPT><<<(unsigned)((N / ZKB_DEEP_RPT + 127) / 128), 128, 0, stream>>>(ab_mat(), dts(), roots, log_tab, d_deep.as<fe>(), 0);
             check_launch();
         } else {
             // multi-GPU: extend and evaluate on this rank's cosets, all-gather the evaluations, restore natural order
@@ -1120,7 +1124,7 @@ struct zkb_ctx {
             ab_log_p = run_xform(x, d_tmp1, d_tmp2);
             d_mg_a.ensure(Nloc * 16); d_mg_b.ensure(N * 16);
             const uint64_t threads = Nloc / ZKB_DEEP_RPT;
-            k_deep_eval<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(ab_mat(), dts(), roots, log_tab, d_mg_a.as<fe>(), 1);
+            k_deep_eval<ZKB_DEEP_RPT><<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(ab_mat(), dts(), roots, log_tab, d_mg_a.as<fe>(), 1);
             check_launch();
             NK(g_nccl.AllGather(d_mg_a.p, d_mg_b.p, Nloc * 16, ncclUint8, comm, stream));
             k_permute_coset_items<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(d_mg_b.as<uint32_t>(), d_deep.as<uint32_t>(), log_n, log_beta,
