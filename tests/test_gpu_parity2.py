@@ -262,3 +262,15 @@ def test_training_2p20_proof_verifies(gpu_ctx, oracle):
     with pytest.raises(RuntimeError):
         oracle.verify(bad, proof)
     pin.free()
+
+
+@pytest.mark.parametrize("w", [65, 128, 129, 192, 193])
+def test_small_domain_leaf_chunk_boundaries(gpu_ctx, oracle, w):
+    """Small LDE domains hash a row's 1 KiB BLAKE3 chunks on separate lanes (k_hash_lde_rows_split) and give every
+    constraint-evaluation point a warp: widths on both sides of the 2-, 3- and 4-chunk boundaries, training-shaped and MiMC AIRs."""
+    n = 16
+    opts = Z.ProofOptions(20, 8, 4, Z.FieldExtension.NONE, 16, 7)
+    data = T.random_felts(w * n, 900 + w).reshape(w, n, 2)
+    _parity(gpu_ctx, oracle, T.synthetic_training_air(n, opts, data), data)
+    air, mdata = _mimc_case(gpu_ctx, oracle, w, 64, opts)
+    _parity(gpu_ctx, oracle, air, mdata)

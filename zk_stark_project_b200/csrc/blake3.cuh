@@ -48,10 +48,28 @@ __host__ __device__ __forceinline__ uint32_t b3_rotr(uint32_t x, int n) {
 #endif
 }
 
+// a + b + m.  The xors and rotations of G can only issue on the ALU pipe (8 of its 12 operations with a + b + m as one
+// IADD3), which is what binds the leaf-hashing kernel (ALU pipe 94-96 % busy, FMA pipe 22 %).  On the device the three-input
+// sums are therefore written as two multiply-adds by a constant-bank 1 that ptxas cannot fold: they issue on the FMA pipe
+// (IMAD), leaving 8 ALU + 6 FMA-pipe operations per G instead of 10 + 2.
+#ifdef __CUDACC__
+__constant__ uint32_t b3_one = 1;
+#endif
+#if defined(__CUDA_ARCH__) && !defined(ZKB_B3_PLAIN_ADDS)
+__device__ __forceinline__ uint32_t b3_add3(uint32_t a, uint32_t b, uint32_t m) {
+    uint32_t t, r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(a), "r"(b3_one), "r"(b));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(t), "r"(b3_one), "r"(m));
+    return r;
+}
+#else
+__host__ __device__ __forceinline__ uint32_t b3_add3(uint32_t a, uint32_t b, uint32_t m) { return a + b + m; }
+#endif
+
 #define B3_G(a, b, c, d, mx, my)      \
-    a = a + b + (mx); d = b3_rotr16(d ^ a); \
+    a = b3_add3(a, b, (mx)); d = b3_rotr16(d ^ a); \
     c = c + d;        b = b3_rotr(b ^ c, 12); \
-    a = a + b + (my); d = b3_rotr8(d ^ a);  \
+    a = b3_add3(a, b, (my)); d = b3_rotr8(d ^ a);  \
     c = c + d;        b = b3_rotr(b ^ c, 7);
 
 #define B3_ROUND(m0, m1, m2, m3, m4, m5, m6, m7, m8, m9, m10, m11, m12, m13, m14, m15) \
