@@ -522,19 +522,31 @@ struct EvalParams {
     LdeMat bnd;
 };
 
+// Row-wise combinations of the trace polynomials (k_boundary_combine, k_deep_combine): ZKB_ROW_LANES lanes share a coefficient row
+#define ZKB_ROW_LANES 8
+__device__ __forceinline__ fe fe_group_sum(fe s) {   // sum over the ZKB_ROW_LANES lanes of a row group; valid on its first lane
+#pragma unroll
+    for (int off = ZKB_ROW_LANES / 2; off > 0; off >>= 1) {
+        fe o;
+        o.x[0] = __shfl_down_sync(0xffffffffu, s.x[0], off, ZKB_ROW_LANES); o.x[1] = __shfl_down_sync(0xffffffffu, s.x[1], off, ZKB_ROW_LANES);
+        o.x[2] = __shfl_down_sync(0xffffffffu, s.x[2], off, ZKB_ROW_LANES); o.x[3] = __shfl_down_sync(0xffffffffu, s.x[3], off, ZKB_ROW_LANES);
+        s = fe_add(s, o);
+    }
+    return s;
+}
 // B_g coefficients: bc[m][g] = sum_{a in group g} coef_a * polys[m][col_a]  (minus sum_a coef_a * value_a at m = 0);
-// one warp per coefficient row, lanes stride over the group's assertions
+// a lane group per coefficient row, its lanes stride over the assertions of each boundary group
 struct BoundaryGroups { uint32_t n_groups; uint32_t g_off[ZKB_MAX_GROUPS + 1]; };
 __global__ void __launch_bounds__(256) k_boundary_combine(const fe* __restrict__ polys, uint32_t n, uint32_t w, const uint32_t* __restrict__ a_col,
                                                           const uint32_t* __restrict__ a_sel, const fe* __restrict__ a_coef, const fe* __restrict__ a_val,
                                                           const BoundaryGroups bg, fe* __restrict__ bc) {
-    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) / ZKB_ROW_LANES, sub = threadIdx.x & (ZKB_ROW_LANES - 1);
     if (row >= n) return;
     const fe* pr = polys + (size_t)row * w;
     for (uint32_t g = 0; g < bg.n_groups; g++) {
         acc288 acc; acc288_zero(acc);
         acc288 cst; acc288_zero(cst);   // row 0 only: sum_a coef_a * value_a
-        for (uint32_t a = bg.g_off[g] + lane; a < bg.g_off[g + 1]; a += 32) {
+        for (uint32_t a = bg.g_off[g] + sub; a < bg.g_off[g + 1]; a += ZKB_ROW_LANES) {
             const uint32_t ai = __ldg(a_sel + a);
             const fe cf = fe_ldg(a_coef + ai);
             acc288_mad(acc, fe_load(pr + __ldg(a_col + a)), cf);
@@ -542,14 +554,8 @@ __global__ void __launch_bounds__(256) k_boundary_combine(const fe* __restrict__
         }
         fe s = acc288_reduce(acc);
         if (row == 0) s = fe_sub(s, acc288_reduce(cst));
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            fe o;
-            o.x[0] = __shfl_down_sync(0xffffffffu, s.x[0], off); o.x[1] = __shfl_down_sync(0xffffffffu, s.x[1], off);
-            o.x[2] = __shfl_down_sync(0xffffffffu, s.x[2], off); o.x[3] = __shfl_down_sync(0xffffffffu, s.x[3], off);
-            s = fe_add(s, o);
-        }
-        if (lane == 0) fe_store(bc + (size_t)row * bg.n_groups + g, s);
+        s = fe_group_sum(s);
+        if (sub == 0) fe_store(bc + (size_t)row * bg.n_groups + g, s);
     }
 }
 
@@ -763,27 +769,24 @@ __global__ void __launch_bounds__(256) k_poly_eval_partial(const fe* __restrict_
 //   A(x) = sum_j gamma_j T_j(x),  B(x) = sum_i gamma'_i H_i(x)
 //   DEEP(x) = (A(x)+B(x) - A(z)-B(z))/(x - z) + (A(x) - A(zg))/(x - zg)
 // which equals Winterfell's coefficient-form quotient at every LDE point.
-// k_deep_combine: AB[m][0] = A coefficients, AB[m][1] = (A+B) coefficients; one warp per coefficient row
+// k_deep_combine: AB[m][0] = A coefficients, AB[m][1] = (A+B) coefficients.  ZKB_ROW_LANES lanes share a coefficient row (its
+// elements are consecutive in memory, so the group reads whole 128-byte lines); with a full warp per row the shuffle reduction
+// and the H tail on one lane cost more issue slots than the w products they serve (ncu, MiMC 2^20: 1.37 ms for a 1 GiB read).
 __global__ void __launch_bounds__(256) k_deep_combine(const fe* __restrict__ polys, uint32_t n, uint32_t w,
                                                       const fe* __restrict__ gamma, const fe* __restrict__ hcoef, uint32_t c,
                                                       const fe* __restrict__ gamma_h, fe* __restrict__ ab) {
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= n) return;
+    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) / ZKB_ROW_LANES, sub = threadIdx.x & (ZKB_ROW_LANES - 1);
+    if (row >= n) return;   // n >= 8: whole warps leave together
     acc288 acc; acc288_zero(acc);
-    for (uint32_t j = lane; j < w; j += 32) acc288_mad(acc, fe_load(polys + (size_t)warp * w + j), fe_ldg(gamma + j));
-    fe s = acc288_reduce(acc);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        fe o;
-        o.x[0] = __shfl_down_sync(0xffffffffu, s.x[0], off); o.x[1] = __shfl_down_sync(0xffffffffu, s.x[1], off);
-        o.x[2] = __shfl_down_sync(0xffffffffu, s.x[2], off); o.x[3] = __shfl_down_sync(0xffffffffu, s.x[3], off);
-        s = fe_add(s, o);
-    }
-    if (lane == 0) {
-        fe b = fe_zero();
-        for (uint32_t i = 0; i < c; i++) b = fe_add(b, fe_mul(fe_load(hcoef + (size_t)i * n + warp), fe_ldg(gamma_h + i)));
-        fe_store(ab + (size_t)warp * 2, s);
-        fe_store(ab + (size_t)warp * 2 + 1, fe_add(s, b));
+    const fe* pr = polys + (size_t)row * w;
+    for (uint32_t j = sub; j < w; j += ZKB_ROW_LANES) acc288_mad(acc, fe_load(pr + j), fe_ldg(gamma + j));
+    acc288 hacc; acc288_zero(hacc);
+    for (uint32_t i = sub; i < c; i += ZKB_ROW_LANES) acc288_mad(hacc, fe_load(hcoef + (size_t)i * n + row), fe_ldg(gamma_h + i));
+    const fe s = fe_group_sum(acc288_reduce(acc));
+    const fe b = c ? fe_group_sum(acc288_reduce(hacc)) : fe_zero();
+    if (sub == 0) {
+        fe_store(ab + (size_t)row * 2, s);
+        fe_store(ab + (size_t)row * 2 + 1, fe_add(s, b));
     }
 }
 // k_deep_eval: each thread handles ZKB_DEEP_RPT rows (one Montgomery batch inversion per thread); RPT = 1 for domains of a

@@ -891,7 +891,7 @@ struct zkb_ctx {
                 for (uint32_t gi = 0; gi <= ng; gi++) bg.g_off[gi] = p.g_off[gi];
                 d_bnd_coef.ensure(n * ng * 16);
                 d_bnd_lde.ensure(n * ce * ng * 16);
-                k_boundary_combine<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(d_polys, (uint32_t)n, ncols, p.a_col, p.a_sel, p.a_coef, p.a_val, bg,
+                k_boundary_combine<<<(unsigned)((n * ZKB_ROW_LANES + 255) / 256), 256, 0, stream>>>(d_polys, (uint32_t)n, ncols, p.a_col, p.a_sel, p.a_coef, p.a_val, bg,
                                                                                         d_bnd_coef.as<fe>());
                 check_launch();
                 Xform xb{d_bnd_coef.as<fe>(), ng, 0, d_bnd_lde.as<fe>(), ng, 0, ng, log_n, false, true, log_n + log_ce, false, HF()};
@@ -1094,13 +1094,13 @@ struct zkb_ctx {
         const fe* gamma = fs_fe(fs.o_gamma);
         d_ab.ensure(n * 2 * 16);
         if (!mg_active) {
-            k_deep_combine<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(d_polys, (uint32_t)n, w, gamma, d_bufA.as<fe>(), c, gamma + w, d_ab.as<fe>());
+            k_deep_combine<<<(unsigned)((n * ZKB_ROW_LANES + 255) / 256), 256, 0, stream>>>(d_polys, (uint32_t)n, w, gamma, d_bufA.as<fe>(), c, gamma + w, d_ab.as<fe>());
             check_launch();
         } else {
             // partial A over this rank's columns -> field all-reduce -> add the (replicated) H part
             const uint32_t wl = w / (uint32_t)mg_world;
             d_mg_a.ensure(n * 2 * 16);
-            k_deep_combine<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(d_polys, (uint32_t)n, wl, gamma + (size_t)mg_rank * wl, d_bufA.as<fe>(), 0,
+            k_deep_combine<<<(unsigned)((n * ZKB_ROW_LANES + 255) / 256), 256, 0, stream>>>(d_polys, (uint32_t)n, wl, gamma + (size_t)mg_rank * wl, d_bufA.as<fe>(), 0,
                                                                               gamma + w, d_mg_a.as<fe>());
             check_launch();
             mg_field_allreduce(d_mg_a.as<fe>(), 2 * n, d_ab.as<fe>());
