@@ -735,7 +735,8 @@ def main():
             "clocks": sampler.summary(t_wall0, t_wall1),
         }
         line.update(roofline_of(args.workload, n, w_local, beta, lde_ms, alg["lde"], peak, peak_src, sharded))
-        line["compute_roofline"]["leaf_hash_alu_pipe_pct"] = 95.8
+        # ncu --set full of the shipped k_hash_lde_rows (profiles/r2_ncu_hash_deep_training_2p16_final.txt)
+        line["compute_roofline"]["leaf_hash_pipes_pct"] = {"alu": 87.7, "fma_heavy": 65.4, "issue_slots": 82.4}
         if headline:
             # BASELINE.json `metric`, first half: prove time of a 2^20-ROW TRACE on one B200, measured in this same run
             line["headline_2p20"] = headline

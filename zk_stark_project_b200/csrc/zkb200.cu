@@ -314,7 +314,7 @@ struct zkb_ctx {
         for (uint32_t q = 0; q < passes; q++) { uint32_t take = (log_len - done + (passes - q) - 1) / (passes - q); done += take; b.push_back(done); }
         return b;
     }
-    // Tile twiddles depend only on (transform size, layer range, coset, t_low): tables of up to 64 MiB are built once per shape
+    // Tile twiddles depend only on (transform size, layer range, coset, t_low): tables of up to 64 MiB (192 MiB for narrow tiles) are built once per shape
     // (k_build_twiddles) and re-read from L2 by every column tile, column group and proof instead of being regenerated
     // (two multiplications per twiddle) by each of the thousands of tiles that share them.
     std::map<std::tuple<uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t>, DevBuf> tw_cache;
@@ -322,11 +322,14 @@ struct zkb_ctx {
     const fe* twiddle_table(const NttPass& p, uint32_t all_cosets) {
         const uint32_t S = 1u << (p.b - p.a);
         const uint64_t entries = ((uint64_t)all_cosets << p.a) * (S - 1u), bytes = entries * 16;
-        if (S < 2 || bytes > ((uint64_t)64 << 20)) return nullptr;
+        // narrow tiles (1-2 columns) have as many twiddles as elements: generating them (two multiplications each) would cost
+        // 40 % on top of the butterflies, so their tables may be larger than those of the wide tiles, which amortise a twiddle
+        // over 4-16 columns
+        if (S < 2 || bytes > ((uint64_t)(pre_twiddles(p.cj) ? 64 : 192) << 20)) return nullptr;
         const auto key = std::make_tuple(p.log_n, p.a, p.b, p.coset, p.inverse, p.coset ? p.log_lde : 0u);
         auto it = tw_cache.find(key);
         if (it != tw_cache.end()) return it->second.as<fe>();
-        if (tw_cache_bytes + bytes > ((uint64_t)256 << 20)) {  // a long-lived context that has seen many shapes: start over
+        if (tw_cache_bytes + bytes > ((uint64_t)768 << 20)) {  // a long-lived context that has seen many shapes: start over
             CK(cudaStreamSynchronize(stream));
             for (auto& kv : tw_cache) kv.second.release();
             tw_cache.clear(); tw_cache_bytes = 0;
