@@ -143,6 +143,12 @@ struct zkb_ctx {
     struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t epoch = 0; uint32_t seen = 0; uint64_t launches = 0; };
     std::map<std::string, GraphEntry> graphs;
     bool capturing = false;
+    // Deferred openings (sharded proofs): every query enqueues its gathers, collectives and a copy into pinned memory and
+    // leaves a finisher behind; the stream is synchronised ONCE for all commitments, then the finishers build rows and paths.
+    bool q_defer = false;
+    size_t q_goff = 0, q_moff = 0, q_hoff = 0;
+    uint8_t* h_q = nullptr; size_t h_q_cap = 0;
+    std::vector<std::function<void()>> q_finish;
     uint8_t* h_out = nullptr;           // pinned landing area of the final download
     size_t h_out_cap = 0;
     cudaEvent_t ev_done = nullptr;      // blocking-sync event: the host thread sleeps instead of spinning while the device works
@@ -224,6 +230,7 @@ struct zkb_ctx {
         if (ev_ok) { for (auto& pr : tev) for (auto& x : pr) cudaEventDestroy(x); for (auto& x : ev_group) cudaEventDestroy(x); cudaStreamDestroy(copy_stream); cudaStreamDestroy(xchg_stream); }
         if (h_stage) cudaFreeHost(h_stage);
         if (h_out) cudaFreeHost(h_out);
+        if (h_q) cudaFreeHost(h_q);
         if (ev_done) cudaEventDestroy(ev_done);
         if (owns_stream && stream) { cudaStreamDestroy(stream); stream = nullptr; }
     }
@@ -259,6 +266,47 @@ struct zkb_ctx {
         CK(cudaStreamSynchronize(stream));
     }
     void check_launch() { CK(cudaGetLastError()); count(); }
+    // scratch of one query: `bytes` of d_gather, `mbytes` of d_mg_b (all-gather landing) — bump-allocated while openings are deferred
+    uint8_t* q_scratch(DevBuf& buf, size_t& off, size_t bytes) {
+        if (!q_defer) { buf.ensure(bytes); return buf.as<uint8_t>(); }
+        const size_t need = (bytes + 255) & ~(size_t)255;
+        if (off + need > buf.cap) throw StateError("internal error: deferred-query scratch exhausted");
+        uint8_t* ptr = buf.as<uint8_t>() + off;
+        off += need;
+        return ptr;
+    }
+    // device -> host read whose consumer `fin(host pointer)` runs now (after a synchronisation) or, deferred, after the batch's one
+    void q_read(const void* dsrc, size_t bytes, std::function<void(const uint8_t*)> fin) {
+        if (!q_defer) {
+            std::vector<uint8_t> host(bytes);
+            d2h(host.data(), dsrc, bytes);
+            fin(host.data());
+            return;
+        }
+        const size_t need = (bytes + 255) & ~(size_t)255;
+        if (q_hoff + need > h_q_cap) throw StateError("internal error: deferred-query landing area exhausted");
+        uint8_t* dst = h_q + q_hoff;
+        q_hoff += need;
+        CK(cudaMemcpyAsync(dst, dsrc, bytes, cudaMemcpyDeviceToHost, stream));
+        q_finish.push_back([fin, dst] { fin(dst); });
+    }
+    void q_begin_batch() {
+        const size_t G = mg_active ? (size_t)mg_world : 1, dev = (size_t)8 << 20;
+        d_gather.ensure(dev); d_mg_b.ensure(dev * G);
+        if (h_q_cap < dev * (G + 1)) {
+            if (h_q) cudaFreeHost(h_q);
+            h_q = nullptr; h_q_cap = 0;
+            CK(cudaHostAlloc((void**)&h_q, dev * (G + 1), cudaHostAllocDefault));
+            h_q_cap = dev * (G + 1);
+        }
+        q_defer = true; q_goff = q_moff = q_hoff = 0; q_finish.clear();
+    }
+    void q_end_batch() {
+        q_defer = false;
+        CK(cudaStreamSynchronize(stream));
+        for (auto& f : q_finish) f();
+        q_finish.clear();
+    }
 
     // ---- tables ---------------------------------------------------------------------------------------------
     static void build_powtab(HF base, uint32_t log_size, std::vector<HF>& lo, std::vector<HF>& hi, uint32_t& l1) {
@@ -723,9 +771,8 @@ struct zkb_ctx {
         }
         const size_t row_bytes = (size_t)np * w * 16, dig_bytes = flat.size() * 32, mine = ((row_bytes + dig_bytes + 15) / 16) * 16;
         size_t o_pos = 0, o_idx = 1024, o_out = o_idx + ((flat.size() * 8 + 15) / 16) * 16 + 16, total = o_out + mine;
-        d_gather.ensure(total);
-        d_mg_b.ensure(mine * G);
-        uint8_t* base = d_gather.as<uint8_t>();
+        uint8_t* base = q_scratch(d_gather, q_goff, total);
+        uint8_t* gathered = q_scratch(d_mg_b, q_moff, mine * G);
         h2d_small(base + o_pos, pos.data(), np * 4);
         if (!flat.empty()) h2d_small(base + o_idx, local.data(), flat.size() * 8);
         k_gather_lde_rows<<<(np * w + 127) / 128, 128, 0, stream>>>(lde_rows_mat(), (const uint32_t*)(base + o_pos), np, (fe*)(base + o_out));
@@ -735,20 +782,21 @@ struct zkb_ctx {
                                                                                         (uint32_t)flat.size(), (uint32_t*)(base + o_out + row_bytes));
             check_launch();
         }
-        NK(g_nccl.AllGather(base + o_out, d_mg_b.p, mine, ncclUint8, comm, stream));
-        std::vector<uint8_t> all(mine * G);
-        d2h(all.data(), d_mg_b.p, all.size());
-        rows.resize(row_bytes);
-        for (uint32_t q = 0; q < np; q++) {
-            const size_t own = pos[q] / Nl;
-            memcpy(&rows[(size_t)q * w * 16], &all[own * mine + (size_t)q * w * 16], (size_t)w * 16);
-        }
-        std::vector<uint8_t> dig(dig_bytes);
-        for (size_t t = 0; t < flat.size(); t++) {
-            if (owner[t] < 0) memcpy(&dig[t * 32], mg_cap[flat[t]].b, 32);
-            else memcpy(&dig[t * 32], &all[(size_t)owner[t] * mine + row_bytes + t * 32], 32);
-        }
-        paths = batch_proof_bytes(log_N, plan, dig.data());
+        NK(g_nccl.AllGather(base + o_out, gathered, mine, ncclUint8, comm, stream));
+        const uint32_t depth = log_N;
+        q_read(gathered, mine * G, [this, pos, plan, flat, owner, np, w, Nl, row_bytes, dig_bytes, mine, depth, &rows, &paths](const uint8_t* all) {
+            rows.resize(row_bytes);
+            for (uint32_t q = 0; q < np; q++) {
+                const size_t own = pos[q] / Nl;
+                memcpy(&rows[(size_t)q * w * 16], all + own * mine + (size_t)q * w * 16, (size_t)w * 16);
+            }
+            std::vector<uint8_t> dig(dig_bytes);
+            for (size_t t = 0; t < flat.size(); t++) {
+                if (owner[t] < 0) memcpy(&dig[t * 32], mg_cap[flat[t]].b, 32);
+                else memcpy(&dig[t * 32], all + (size_t)owner[t] * mine + row_bytes + t * 32, 32);
+            }
+            paths = batch_proof_bytes(depth, plan, dig.data());
+        });
     }
 
     // ---- Fiat-Shamir steps.  `digest` = device address of the commitment the coin is reseeded with (one-shot proofs: the whole
@@ -1265,8 +1313,7 @@ struct zkb_ctx {
         // device scratch: [positions np u32][idx flat u64][rows np*width fe][digests flat*32]
         size_t o_pos = 0, o_idx = 1024, o_rows = o_idx + ((flat.size() * 8 + 15) / 16) * 16 + 16, o_dig = o_rows + (size_t)np * width * 16,
                total = o_dig + flat.size() * 32 + 32;
-        d_gather.ensure(total);
-        uint8_t* base = d_gather.as<uint8_t>();
+        uint8_t* base = q_scratch(d_gather, q_goff, total);
         h2d_small(base + o_pos, pos.data(), np * 4);
         if (!flat.empty()) h2d_small(base + o_idx, flat.data(), flat.size() * 8);
         const uint32_t th = np * width;
@@ -1283,22 +1330,25 @@ struct zkb_ctx {
                                                                                         (uint32_t*)(base + o_dig));
             check_launch();
         }
-        std::vector<uint8_t> host((size_t)np * width * 16 + flat.size() * 32);
-        d2h(host.data(), base + o_rows, host.size());  // rows and digests are adjacent
-        rows.assign(host.begin(), host.begin() + (size_t)np * width * 16);
+        const size_t rows_bytes = (size_t)np * width * 16;
+        // rows and digests are adjacent
+        q_read(base + o_rows, rows_bytes + flat.size() * 32, [this, plan, depth, rows_bytes, &rows, &paths](const uint8_t* host) {
+            rows.assign(host, host + rows_bytes);
+            paths = batch_proof_bytes(depth, plan, host + rows_bytes);
+        });
         if (which == 1 && mg_coset()) {
             // coset-sharded composition LDE: a queried row lives on the rank that owns its coset (the tree is replicated)
-            const size_t rb = (((size_t)np * width * 16 + 15) / 16) * 16;
-            d_mg_b.ensure(rb * mg_world);
-            NK(g_nccl.AllGather(base + o_rows, d_mg_b.p, rb, ncclUint8, comm, stream));
-            std::vector<uint8_t> all(rb * mg_world);
-            d2h(all.data(), d_mg_b.p, all.size());
-            for (uint32_t q = 0; q < np; q++) {
-                const size_t own = (pos[q] & (air.blowup - 1)) >> mg_log_kc();
-                memcpy(&rows[(size_t)q * width * 16], &all[own * rb + (size_t)q * width * 16], (size_t)width * 16);
-            }
+            const size_t rb = ((rows_bytes + 15) / 16) * 16;
+            uint8_t* gathered = q_scratch(d_mg_b, q_moff, rb * mg_world);
+            NK(g_nccl.AllGather(base + o_rows, gathered, rb, ncclUint8, comm, stream));
+            const uint32_t blow = (uint32_t)air.blowup, lkc = mg_log_kc();
+            q_read(gathered, rb * mg_world, [pos, np, width, rb, blow, lkc, &rows](const uint8_t* all) {   // runs after the reader above
+                for (uint32_t q = 0; q < np; q++) {
+                    const size_t own = (pos[q] & (blow - 1)) >> lkc;
+                    memcpy(&rows[(size_t)q * width * 16], all + own * rb + (size_t)q * width * 16, (size_t)width * 16);
+                }
+            });
         }
-        paths = batch_proof_bytes(depth, plan, host.data() + (size_t)np * width * 16);
     }
 
     // ==========================================================================================================
@@ -1573,9 +1623,13 @@ struct zkb_ctx {
                 fpos[l] = fold_positions(l ? fpos[l - 1] : positions, dom, 16);
                 dom /= 16;
             }
-            for (uint32_t l = 0; l < fri_layers; l++) query(2 + l, fpos[l], parts.fri_rows[l], parts.fri_paths[l]);
-            query(0, positions, parts.trace_rows, parts.trace_paths);
-            query(1, positions, parts.comp_rows, parts.comp_paths);
+            q_begin_batch();   // seven commitments, two all-gathers, one synchronisation
+            try {
+                for (uint32_t l = 0; l < fri_layers; l++) query(2 + l, fpos[l], parts.fri_rows[l], parts.fri_paths[l]);
+                query(0, positions, parts.trace_rows, parts.trace_paths);
+                query(1, positions, parts.comp_rows, parts.comp_paths);
+            } catch (...) { q_defer = false; q_finish.clear(); throw; }
+            q_end_batch();
         }
         t_end(TS_QUERY);
         t_end(TS_TOTAL);
