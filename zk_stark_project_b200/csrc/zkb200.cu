@@ -45,6 +45,7 @@ namespace zkb {
 // replayed while the epoch it was captured in is still current
 static std::atomic<uint64_t> g_alloc_epoch{1};
 
+#define ZKB_CAP_BYTES 4096   // 2 G digests of the replicated Merkle cap of a sharded trace commitment (G <= 64)
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -157,6 +158,7 @@ struct zkb_ctx {
     const fe* d_aval() const { return d_in.as<fe>(); }
     const fe* d_params() const { return d_in.as<fe>() + air.assertions.size(); }
     DevBuf d_lde_rows, d_mg_a, d_mg_b;  // recv view of the LDE; all-gather staging
+    DevBuf d_cap;                       // sharded trace commitment: heap of the replicated top log G levels on the device
     std::vector<Digest32> mg_cap;       // heap of the replicated top log G levels: cap[1] = root, cap[G + q] = subtree root q
 
     // ==========================================================================================================
@@ -218,7 +220,7 @@ struct zkb_ctx {
         cudaStreamSynchronize(stream);
         for (DevBuf* b : {&d_trace, &d_bufA, &d_bufB, &d_tmp1, &d_tmp2, &d_lde, &d_tree, &d_small, &d_comp_evals, &d_comp_lde, &d_comp_tree,
                           &d_ab, &d_ab_lde, &d_deep, &d_roots_lo, &d_roots_hi, &d_inv3_lo, &d_inv3_hi, &d_pow3, &d_aux, &d_gather, &d_user_trace, &d_flags,
-                          &d_lde_rows, &d_mg_a, &d_mg_b, &d_bnd_coef, &d_bnd_lde, &d_fs, &d_in, &d_rem_coef})
+                          &d_lde_rows, &d_mg_a, &d_mg_b, &d_cap, &d_bnd_coef, &d_bnd_lde, &d_fs, &d_in, &d_rem_coef})
             b->release();
         if (comm) { g_nccl.CommDestroy(comm); comm = nullptr; }
         for (auto& b : d_fri_evals) b.release();
@@ -539,11 +541,11 @@ struct zkb_ctx {
             fs.total = off;
             d_fs.ensure(fs.total);
             d_flags.ensure(256);
-            if (h_out_cap < fs.host_bytes) {
+            if (h_out_cap < fs.host_bytes + ZKB_CAP_BYTES) {   // + landing area of a sharded proof's commitment cap
                 if (h_out) { cudaFreeHost(h_out); h_out = nullptr; h_out_cap = 0; }
                 g_alloc_epoch++;
-                CK(cudaHostAlloc((void**)&h_out, fs.host_bytes, cudaHostAllocDefault));
-                h_out_cap = fs.host_bytes;
+                CK(cudaHostAlloc((void**)&h_out, fs.host_bytes + ZKB_CAP_BYTES, cudaHostAllocDefault));
+                h_out_cap = fs.host_bytes + ZKB_CAP_BYTES;
             }
             // transcript: coin seed = hash(Context ++ public inputs), computed here because the host holds the AIR; all else zero
             DevTs h0;
@@ -735,19 +737,25 @@ struct zkb_ctx {
         t_end(TS_LEAF);
         t_begin(TS_MERKLE);
         build_merkle(d_tree.as<uint32_t>(), Nl);
-        // all-gather of the subtree roots; the cap is finished on the host by every rank
-        d_gather.ensure(4096 + (size_t)G * 32);
-        NK(g_nccl.AllGather(d_tree.as<uint8_t>() + 32, d_gather.as<uint8_t>(), 32, ncclUint8, comm, stream));
+        // all-gather of the subtree roots into the leaves of the cap heap, which every rank finishes: cap[1] = root
+        if (2 * (size_t)G * 32 > ZKB_CAP_BYTES) throw InvalidArg("too many GPUs for one sharded commitment");
+        d_cap.ensure(ZKB_CAP_BYTES);
+        NK(g_nccl.AllGather(d_tree.as<uint8_t>() + 32, d_cap.as<uint8_t>() + (size_t)G * 32, 32, ncclUint8, comm, stream));
+        k_merkle_top<<<1, 512, 0, stream>>>(d_cap.as<uint32_t>(), G / 2);
+        check_launch();
         t_end(TS_MERKLE);
+        // (the `interpolate` slot of zkb_stage_times carries the NVLink all-to-all time of a sharded proof)
+        stage = ST_TRACE;
+        if (!root_out) {   // one-shot sharded proof: the channel reads the root on the device; the host copy of the cap (openings) rides along
+            CK(cudaMemcpyAsync(h_out + fs.host_bytes, d_cap.p, 2 * (size_t)G * 32, cudaMemcpyDeviceToHost, stream));
+            return;
+        }
         mg_cap.assign(2 * (size_t)G, Digest32{});
-        d2h(mg_cap.data() + G, d_gather.p, (size_t)G * 32);
-        for (uint32_t i = G - 1; i >= 1; i--) { uint8_t buf[64]; memcpy(buf, mg_cap[2 * i].b, 32); memcpy(buf + 32, mg_cap[2 * i + 1].b, 32); b3_hash_host(buf, 64, mg_cap[i].b); }
+        d2h(mg_cap.data(), d_cap.p, 2 * (size_t)G * 32);
         const Digest32 root = mg_cap[1];
         parts.commitments.push_back(root);
         memcpy(ts.trace_root, root.b, 32);
-        if (root_out) memcpy(root_out, root.b, 32);
-        // (the `interpolate` slot of zkb_stage_times carries the NVLink all-to-all time of a sharded proof)
-        stage = ST_TRACE;
+        memcpy(root_out, root.b, 32);
     }
     // TraceLde::query for a sharded trace: every rank gathers the queried rows / authentication nodes it owns, the
     // contributions are all-gathered and the owner's copy of each entry is kept.
@@ -1448,26 +1456,8 @@ struct zkb_ctx {
         ood_eval_dev();
         fs_after_ood(true, nullptr);                                   // send_ood_*; get_deep_composition_coeffs
         deep_compose_dev();
-        t_begin(TS_FRI);
-        for (uint32_t l = 0; l < fri_layers; l++) {                    // FriProver::build_layers
-            fri_commit_layer_dev();
-            k_fs_fri_root<<<1, 32, 0, stream>>>(dts(), d_fri_tree[l].as<uint32_t>() + 8, l);
-            check_launch();
-            fri_fold_dev();
-        }
-        fri_remainder_dev(true);
-        t_end(TS_FRI);
-        t_begin(TS_GRIND);
-        if (force_nonce) { const unsigned long long v = force_nonce; h2d_small(&dts()->nonce, &v, 8); }
-        else {                                                         // grind_query_seed
-            k_fs_grind<<<(unsigned)sm_count * 8, 256, 0, stream>>>(dts(), air.grinding, 1ull << 44);
-            check_launch();
-        }
-        t_end(TS_GRIND);
-        t_begin(TS_QUERY);
+        enqueue_fri_to_positions(force_nonce);
         const uint32_t q = air.num_queries;
-        k_fs_positions<<<1, ZKB_FS_THREADS, 0, stream>>>(dts(), q, (uint32_t)(air.lde_size() - 1));   // get_query_positions
-        check_launch();
         {   // TraceLde::query, ConstraintCommitment::query, FriProver::build_proof at the raw positions: one launch
             OpenJobs J{};
             uint8_t* base = d_fs.as<uint8_t>();
@@ -1495,10 +1485,35 @@ struct zkb_ctx {
         CK(cudaMemcpyAsync(h_out, d_fs.p, fs.host_bytes, cudaMemcpyDeviceToHost, stream));
     }
 
+    // FRI layers, remainder, proof of work and query positions: replicated on every rank of a sharded proof
+    void enqueue_fri_to_positions(uint64_t force_nonce) {
+        t_begin(TS_FRI);
+        for (uint32_t l = 0; l < fri_layers; l++) {                    // FriProver::build_layers
+            fri_commit_layer_dev();
+            k_fs_fri_root<<<1, 32, 0, stream>>>(dts(), d_fri_tree[l].as<uint32_t>() + 8, l);
+            check_launch();
+            fri_fold_dev();
+        }
+        fri_remainder_dev(true);
+        t_end(TS_FRI);
+        t_begin(TS_GRIND);
+        if (force_nonce) { const unsigned long long v = force_nonce; h2d_small(&dts()->nonce, &v, 8); }
+        else {                                                         // grind_query_seed
+            k_fs_grind<<<(unsigned)sm_count * 8, 256, 0, stream>>>(dts(), air.grinding, 1ull << 44);
+            check_launch();
+        }
+        t_end(TS_GRIND);
+        t_begin(TS_QUERY);
+        k_fs_positions<<<1, ZKB_FS_THREADS, 0, stream>>>(dts(), air.num_queries, (uint32_t)(air.lde_size() - 1));   // get_query_positions
+        check_launch();
+    }
+
     // Proof assembly from the single download: sort / dedup the positions (get_query_positions), fold them per FRI layer
     // (fold_positions), select rows, and build every BatchMerkleProof from the full paths gathered on the device — each node of
     // a batch proof is the sibling of an ancestor of some queried leaf, so it is in one of those paths.
-    std::vector<uint8_t> assemble_proof() {
+    // transcript, commitments, OOD frame, remainder, nonce and the sorted / deduplicated positions from the single download;
+    // returns the raw positions
+    std::vector<uint32_t> assemble_transcript() {
         const DevTs* h = reinterpret_cast<const DevTs*>(h_out);
         if (h->coin_failed) throw std::runtime_error("random coin failed to draw a field element");
         if (h->nonce == ~0ull) throw std::runtime_error("proof-of-work nonce not found");
@@ -1531,6 +1546,11 @@ struct zkb_ctx {
         parts.n_unique = (uint32_t)positions.size();
         ts.n_positions = parts.n_unique;
         for (size_t i = 0; i < positions.size() && i < 256; i++) ts.positions[i] = positions[i];
+        return raw;
+    }
+    std::vector<uint8_t> assemble_proof() {
+        const std::vector<uint32_t> raw = assemble_transcript();
+        const uint32_t q = air.num_queries;
         // one commitment: rows of `pos` (each found among the raw positions reduced by `mask`) + batch proof
         auto open = [&](const FsTree& tr, const std::vector<uint32_t>& pos, uint32_t mask, std::vector<uint8_t>& rows, std::vector<uint8_t>& paths) {
             const uint8_t* hrows = h_out + tr.o_rows;
@@ -1573,7 +1593,7 @@ struct zkb_ctx {
     }
 
     // column-sharded proof: the channel stays on the host (every rank replays it identically between the collectives)
-    std::vector<uint8_t> prove_sharded(const uint8_t* const* cols, const fe* d_trace_in, uint64_t force_nonce) {
+    void prove_sharded_host_coin(const uint8_t* const* cols, const fe* d_trace_in, uint64_t force_nonce) {
         uint8_t root[32];
         trace_commit_mg(cols, d_trace_in, root);
         coin.reseed(root);                                   // channel.commit_trace
@@ -1607,14 +1627,41 @@ struct zkb_ctx {
         t_begin(TS_GRIND);
         uint64_t nonce = force_nonce ? force_nonce : grind(coin.seed, air.grinding);  // grind_query_seed
         t_end(TS_GRIND);
-        t_begin(TS_QUERY);
         parts.nonce = nonce; ts.pow_nonce = nonce;
+        t_begin(TS_QUERY);
         positions = coin.draw_integers(air.num_queries, air.lde_size(), nonce);        // get_query_positions
         std::sort(positions.begin(), positions.end());
         positions.erase(std::unique(positions.begin(), positions.end()), positions.end());
         parts.n_unique = (uint32_t)positions.size();
         ts.n_positions = parts.n_unique;
         for (size_t i = 0; i < positions.size() && i < 256; i++) ts.positions[i] = positions[i];
+    }
+    // Column-sharded proof.  The channel is replicated on the device of every rank (csrc/coin.cuh: all ranks see the same
+    // commitments, OOD frame and remainder, so they draw the same challenges), as in the single-GPU proof: no host round trip
+    // until the query positions are known; then the openings of all commitments are gathered from their owners in one batch.
+    // ZKB_MG_HOST_COIN=1 keeps the channel on the host, one synchronisation per commitment (the round-1 path; A/B and the staged API).
+    std::vector<uint8_t> prove_sharded(const uint8_t* const* cols, const fe* d_trace_in, uint64_t force_nonce) {
+        static const bool host_coin = getenv("ZKB_MG_HOST_COIN") != nullptr;
+        if (host_coin) prove_sharded_host_coin(cols, d_trace_in, force_nonce);
+        else {
+            trace_commit_mg(cols, d_trace_in, nullptr);
+            fs_after_trace_root(d_cap.as<uint32_t>() + 8, nullptr);        // channel.commit_trace; get_constraint_composition_coeffs
+            constraints_eval_dev();
+            constraints_commit_dev();
+            fs_after_constraint_root(d_comp_tree.as<uint32_t>() + 8, nullptr);   // channel.commit_constraints; get_ood_point
+            ood_eval_dev();
+            fs_after_ood(true, nullptr);                                   // send_ood_*; get_deep_composition_coeffs
+            deep_compose_dev();
+            enqueue_fri_to_positions(force_nonce);
+            // transcript, OOD frame, remainder (not the opening areas behind them, which a sharded proof does not fill)
+            const size_t head = fs.trees.empty() ? fs.host_bytes : std::min(fs.host_bytes, fs.trees[0].o_rows);
+            CK(cudaMemcpyAsync(h_out, d_fs.p, head, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));   // spin: the openings are enqueued the moment the positions are known
+            const size_t G = (size_t)mg_world;
+            mg_cap.assign(2 * G, Digest32{});
+            memcpy(mg_cap.data(), h_out + fs.host_bytes, 2 * G * 32);
+            assemble_transcript();
+        }
         {   // FriProver::build_proof, TraceLde::query, ConstraintCommitment::query
             std::vector<std::vector<uint32_t>> fpos(fri_layers);
             uint64_t dom = air.lde_size();
