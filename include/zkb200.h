@@ -170,6 +170,8 @@ int32_t zkb_query(zkb_ctx* ctx, uint32_t which, const uint32_t* positions, uint3
  * local; an NCCL all-to-all over NVLink turns column shards into row shards for leaf hashing and the Merkle subtrees, whose
  * roots are all-gathered; constraint evaluation, OOD and DEEP are column-local partial sums combined by an all-gather.
  * `air` describes the WHOLE trace (global width, all assertions); `local_cols` holds this rank's w/G columns.
+ * The Fiat-Shamir channel runs replicated on every rank's device (all ranks hold the same commitments, OOD frame and
+ * remainder); the host is met twice per proof: for the query positions and for the batched openings.
  * Every rank returns the same proof bytes.  G must be a power of two that divides w (and at most the LDE panel size);
  * the aggregation AIR couples columns i and i+60 and is not shardable. */
 int32_t zkb_mg_unique_id(uint8_t out[128]);                                         /* ncclGetUniqueId, on rank 0 */

@@ -1365,7 +1365,7 @@ struct zkb_ctx {
     // (transcript, OOD frame, remainder, and for every commitment the rows and full authentication paths at the raw query
     // positions, from which the host picks what BatchMerkleProof needs after sorting / deduplicating the positions).
     // sharded = true: `cols` / `d_trace_in` hold only this rank's w/G columns and the proof is produced cooperatively by all
-    // ranks of the NCCL communicator with the channel on the host (every rank returns the same bytes).
+    // ranks of the NCCL communicator, the channel replicated on every rank's device (every rank returns the same bytes).
     std::vector<uint8_t> prove(const zkb_air_desc* desc, const uint8_t* const* cols, const fe* d_trace_in, uint64_t force_nonce,
                                bool sharded = false) {
         static const bool host_prof = getenv("ZKB_HOST_PROFILE") != nullptr;   // diagnostics: host phases of a proof on stderr
@@ -1592,7 +1592,8 @@ struct zkb_ctx {
         return serialize_proof(air, parts);
     }
 
-    // column-sharded proof: the channel stays on the host (every rank replays it identically between the collectives)
+    // column-sharded proof with the channel on the host (every rank replays it identically between the collectives): the round-1
+    // flow, kept behind ZKB_MG_HOST_COIN=1 for A/B measurements
     void prove_sharded_host_coin(const uint8_t* const* cols, const fe* d_trace_in, uint64_t force_nonce) {
         uint8_t root[32];
         trace_commit_mg(cols, d_trace_in, root);
