@@ -779,7 +779,16 @@ __global__ void __launch_bounds__(256) k_deep_combine(const fe* __restrict__ pol
     if (row >= n) return;   // n >= 8: whole warps leave together
     acc288 acc; acc288_zero(acc);
     const fe* pr = polys + (size_t)row * w;
-    for (uint32_t j = sub; j < w; j += ZKB_ROW_LANES) acc288_mad(acc, fe_load(pr + j), fe_ldg(gamma + j));
+    // four loads in flight per lane: the loop is bound by load latency, not by the products (ncu: long-scoreboard stalls)
+    uint32_t j = sub;
+    for (; j + 3 * ZKB_ROW_LANES < w; j += 4 * ZKB_ROW_LANES) {
+        const fe v0 = fe_load(pr + j), v1 = fe_load(pr + j + ZKB_ROW_LANES), v2 = fe_load(pr + j + 2 * ZKB_ROW_LANES), v3 = fe_load(pr + j + 3 * ZKB_ROW_LANES);
+        acc288_mad(acc, v0, fe_ldg(gamma + j));
+        acc288_mad(acc, v1, fe_ldg(gamma + j + ZKB_ROW_LANES));
+        acc288_mad(acc, v2, fe_ldg(gamma + j + 2 * ZKB_ROW_LANES));
+        acc288_mad(acc, v3, fe_ldg(gamma + j + 3 * ZKB_ROW_LANES));
+    }
+    for (; j < w; j += ZKB_ROW_LANES) acc288_mad(acc, fe_load(pr + j), fe_ldg(gamma + j));
     acc288 hacc; acc288_zero(hacc);
     for (uint32_t i = sub; i < c; i += ZKB_ROW_LANES) acc288_mad(hacc, fe_load(hcoef + (size_t)i * n + row), fe_ldg(gamma_h + i));
     const fe s = fe_group_sum(acc288_reduce(acc));
